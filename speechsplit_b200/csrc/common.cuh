@@ -1,0 +1,150 @@
+// common.cuh - shared declarations of libssfe.so (context, workspace, helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/ssfe.h"
+
+namespace ssfe {
+
+constexpr int kFs = 16000;
+constexpr int kNfft = 1024;
+constexpr int kHop = 256;
+constexpr int kBins = 513;
+constexpr int kMels = 80;
+constexpr int kHalfPad = 512;          // reflect pad of pySTFT (utils.py:20)
+constexpr int kSegAlign = 64;          // padded-wav segments start on 256-byte boundaries
+constexpr int kSegSlack = 2048;        // floats readable past a segment (tile over-read)
+constexpr float kUnvoiced = -1.0e10f;  // make_spect_f0.py:65
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+// grow-only device scratch; growth happens during warm-up only
+struct Workspace {
+    DevBuf wavp, y1, dith, meta_dev, tiles, misc;
+    DevBuf rapt_ds, rapt_cand, rapt_stat, rapt_f0;
+    DevBuf carry;
+};
+
+struct MelTables {
+    int n_entries = 0;                 // E: entries per lane (padded)
+    int n_seg = 0;                     // segments per lane
+    int2 *ent = nullptr;               // [E][32] (bin index, weight bits); weight already * 0.5
+    int2 *seg = nullptr;               // [n_seg][32] (end entry, band or -1)
+};
+
+struct RaptTables;                     // rapt.cu
+
+}  // namespace ssfe
+
+struct ssfe_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;      // ssfe_extract_host pipeline
+    ssfe_config cfg;
+    std::vector<float> mel_basis;      // host copy (513 x 80)
+    char err[512];
+    int64_t launches = 0;
+    // pinned <-> device metadata arena (bump allocated, reset after a stream sync when full)
+    char *meta_host = nullptr;
+    char *meta_dev = nullptr;
+    size_t meta_cap = 0, meta_used = 0;
+    // tables
+    float *d_window = nullptr;         // periodic Hann(1024)
+    float2 *d_tw = nullptr;            // [k1][lane] = exp(-2 pi i lane k1 / 1024)
+    ssfe::MelTables mel;
+    double *d_filt = nullptr;          // filtfilt constants (see filtfilt.cu)
+    ssfe::RaptTables *rapt = nullptr;
+    ssfe::Workspace ws;
+    // host staging for ssfe_extract_host
+    void *pin_in = nullptr;  size_t pin_in_cap = 0;
+    void *pin_out = nullptr; size_t pin_out_cap = 0;
+    ssfe::DevBuf h_x, h_mel, h_f0, h_bins;
+};
+
+namespace ssfe {
+
+int set_error(ssfe_ctx *ctx, int code, const char *fmt, ...);
+int cuda_fail(ssfe_ctx *ctx, cudaError_t e, const char *what);
+int ensure(ssfe_ctx *ctx, DevBuf &b, size_t bytes);
+// copies `bytes` of host metadata to the device through the pinned arena; returns device pointer
+void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes);
+template <typename T>
+inline T *upload(ssfe_ctx *ctx, const T *host, size_t n)
+{
+    return static_cast<T *>(upload_meta(ctx, host, n * sizeof(T)));
+}
+
+#define SSFE_CUDA(ctx, expr)                                            \
+    do {                                                                \
+        cudaError_t e__ = (expr);                                       \
+        if (e__ != cudaSuccess) return ::ssfe::cuda_fail(ctx, e__, #expr); \
+    } while (0)
+
+#define SSFE_LAUNCHED(ctx)                                              \
+    do {                                                                \
+        (ctx)->launches++;                                              \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) return ::ssfe::cuda_fail(ctx, e__, "kernel launch"); \
+    } while (0)
+
+// index of the segment containing pos: largest i with off[i] <= pos (off has n+1 entries)
+template <typename T>
+__device__ __forceinline__ int find_segment(const T *__restrict__ off, int n, T pos)
+{
+    int lo = 0, hi = n;     // invariant: off[lo] <= pos < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- stage implementations (internal, called by api.cu) ------------------------------------
+int init_stft_tables(ssfe_ctx *ctx);
+void free_stft_tables(ssfe_ctx *ctx);
+// wav (f32, unpadded, offsets dev/host) -> reflect-padded layout in ws.wavp; fills seg_off
+int pad_reflect(ssfe_ctx *ctx, const float *wav_dev, const int64_t *offsets_host, int n,
+                std::vector<int64_t> &seg_off_host);
+// fused kernel over an already padded buffer.  mode 0: mel-dB (out [F,80]); 1: magnitude (out [F,513])
+int stft_padded(ssfe_ctx *ctx, const float *wavp, const int64_t *seg_off_host,
+                const int64_t *frames_host /* [n] frames per utterance */, int n, int mode, float *out);
+
+int init_filtfilt(ssfe_ctx *ctx);
+void free_filtfilt(ssfe_ctx *ctx);
+// x (dtype) -> y f64 [fixed offsets].  If wavp != nullptr also fuses  wav = 0.96*y + dith  into the
+// backward pass and writes it (f32) into the padded layout / wav_out / wav64_out.
+struct FiltOut {
+    double *y = nullptr;             // filtfilt output (may be null when fused outputs requested)
+    const double *dith = nullptr;    // uniform doubles U (fixed offsets); wav = y*0.96 + (U-0.5)*1e-6
+    float *wavp = nullptr;           // padded layout base
+    const int64_t *seg_off_dev = nullptr;
+    float *wav = nullptr;            // flat f32 [fixed offsets]
+    double *wav64 = nullptr;
+};
+int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_off_host,
+                 const int64_t *fix_off_host, int n, const FiltOut &out);
+int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
+                       const int64_t *fix_off_dev, int n);
+
+int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
+             int n, double *u_dev);
+
+int init_rapt(ssfe_ctx *ctx);
+void free_rapt(ssfe_ctx *ctx);
+// wav source: either flat f32 (wav_dev + offsets) or padded layout (wavp + seg_off, data at +512)
+int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host /* [n] first sample */,
+             const int64_t *len_host /* [n] */, const int64_t *frame_off_host /* [n+1] */, int n,
+             const float *f0_lo, const float *f0_hi, float *f0_dev);
+
+// a7+a8 (+a9 when bins/onehot given) over a ragged batch; frame offsets are HOST [n+1]
+int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_host, int n,
+                float *f0_norm_dev, float *stats_dev, float *onehot, int64_t *bins);
+
+}  // namespace ssfe

@@ -1,0 +1,319 @@
+// f0_post.cu - stages a7, a8, a9 and the collator.
+//
+//   a7  make_spect_f0.py:65-66  index_nonzero = f0 != -1e10; np.mean / np.std of the voiced
+//       log-F0 of THIS utterance.  The array is float32, so numpy reduces in float32 with its
+//       pairwise summation (blocks of <=128 with 8 accumulators, halves rounded down to a
+//       multiple of 8); that exact order is reproduced so the statistics are bit-identical.
+//   a8  utils.speaker_normalization (utils.py:35-42) in float64, stored float32 (:73-74).
+//   a9  utils.quantize_f0_numpy / quantize_f0_torch (utils.py:46-74): uv = x<=0 -> bin 0,
+//       else round-half-even(x*num_bins-...)+1, one-hot float32.
+//   collator: data_loader.py:101-128 (crop, clip [0,1], zero-pad to 192, F0 pad -1e10) feeding
+//       solver.py:160-163.
+#include "common.cuh"
+#include <algorithm>
+
+namespace ssfe {
+
+// ---- numpy float32 pairwise sum (numpy/_core/src/umath/loops_utils.h.src semantics) -----------
+__device__ float np_pairwise_sum_f32(const float *a, int n)
+{
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    } else if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return __fadd_rn(np_pairwise_sum_f32(a, n2), np_pairwise_sum_f32(a + n2, n - n2));
+    }
+}
+
+// one thread per utterance: compact the voiced frames, then float32 mean and std (ddof = 0)
+__global__ void f0_stats_kernel(const float *__restrict__ f0, const int64_t *__restrict__ frame_off, int n,
+                                float *__restrict__ scratch, float *__restrict__ stats /* [n][2] */)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int64_t beg = frame_off[u];
+    const int T = static_cast<int>(frame_off[u + 1] - beg);
+    float *buf = scratch + beg;
+    int nv = 0;
+    for (int t = 0; t < T; ++t) {
+        const float v = f0[beg + t];
+        if (v != kUnvoiced) buf[nv++] = v;
+    }
+    float mean, sd;
+    if (nv == 0) {   // np.mean of an empty selection: nan (RuntimeWarning), make_spect_f0.py:66
+        mean = __int_as_float(0x7fc00000);
+        sd = mean;
+    } else {
+        const float cnt = static_cast<float>(nv);
+        mean = __fdiv_rn(__fadd_rn(0.0f, np_pairwise_sum_f32(buf, nv)), cnt);
+        for (int i = 0; i < nv; ++i) {
+            const float d = __fsub_rn(buf[i], mean);
+            buf[i] = __fmul_rn(d, d);
+        }
+        const float var = __fdiv_rn(__fadd_rn(0.0f, np_pairwise_sum_f32(buf, nv)), cnt);
+        sd = __fsqrt_rn(var);
+    }
+    stats[2 * u] = mean;
+    stats[2 * u + 1] = sd;
+}
+
+__device__ __forceinline__ long long quantize_value(double x, int num_bins, bool *bad)
+{
+    // utils.py:50-55.  NaN: (x<=0) is false and the range assert fails in the reference.
+    if (x <= 0.0) return 0;
+    if (!(x <= 1.0)) {
+        *bad = true;
+        return 0;
+    }
+    return static_cast<long long>(rint(x * static_cast<double>(num_bins - 1))) + 1;
+}
+
+// per frame: speaker_normalization with the utterance's stats, then the bin of the stored f32 value
+__global__ void f0_norm_quant_kernel(const float *__restrict__ f0, const int64_t *__restrict__ frame_off,
+                                     int n, const float *__restrict__ stats, int64_t total,
+                                     float *__restrict__ f0_norm, int64_t *__restrict__ bins)
+{
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= total) return;
+    const int u = find_segment(frame_off, n, t);
+    const float v = f0[t];
+    float o = v;
+    if (v != kUnvoiced) {
+        const double mean = stats[2 * u], sd = stats[2 * u + 1];
+        double z = __ddiv_rn(__ddiv_rn(__dsub_rn(static_cast<double>(v), mean), sd), 4.0);   // utils.py:38
+        const bool isnan_z = (z != z);                                                        // np.clip keeps nan
+        z = fmin(fmax(z, -1.0), 1.0);                                                         // :39
+        if (isnan_z) z = __longlong_as_double(0x7ff8000000000000LL);
+        o = static_cast<float>(__ddiv_rn(__dadd_rn(z, 1.0), 2.0));                            // :40, saved f32
+    }
+    if (f0_norm) f0_norm[t] = o;
+    if (bins) {
+        bool bad = false;
+        bins[t] = quantize_value(static_cast<double>(o), 256, &bad);
+    }
+}
+
+template <typename T>
+__global__ void quantize_kernel(const T *__restrict__ x, int64_t count, int num_bins,
+                                int64_t *__restrict__ bins, int *__restrict__ bins32, int *__restrict__ bad_flag)
+{
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= count) return;
+    bool bad = false;
+    const long long b = quantize_value(static_cast<double>(x[t]), num_bins, &bad);
+    if (bad) atomicExch(bad_flag, 1);
+    if (bins) bins[t] = b;
+    bins32[t] = static_cast<int>(b);
+}
+
+// one-hot rows: out[t][c] = (c == bin[t]); float4 stores where the row start allows it
+template <typename B>
+__global__ void onehot_kernel(const B *__restrict__ bins, int64_t count, int width, float *__restrict__ out)
+{
+    const int64_t total = count * width;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = i / width;
+        const int c = static_cast<int>(i - t * width);
+        out[i] = (static_cast<int>(bins[t]) == c) ? 1.0f : 0.0f;
+    }
+}
+
+template <typename T>
+__global__ void speaker_norm_kernel(const T *__restrict__ f0, const uint8_t *__restrict__ nz, double mean,
+                                    double sd, int64_t count, double *__restrict__ out)
+{
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= count) return;
+    double v = static_cast<double>(f0[t]);
+    if (nz[t]) {
+        double z = __ddiv_rn(__ddiv_rn(__dsub_rn(v, mean), sd), 4.0);
+        const bool isnan_z = (z != z);
+        z = fmin(fmax(z, -1.0), 1.0);
+        if (isnan_z) z = __longlong_as_double(0x7ff8000000000000LL);
+        v = __ddiv_rn(__dadd_rn(z, 1.0), 2.0);
+    }
+    out[t] = v;
+}
+
+}  // namespace ssfe
+
+using namespace ssfe;
+
+static int64_t grid_for(int64_t work, int threads) { return (work + threads - 1) / threads; }
+
+namespace ssfe {
+int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_host, int n, float *f0_norm_dev,
+                float *stats_dev, float *onehot, int64_t *bins)
+{
+    const int64_t total = frame_off_host[n];
+    if (n == 0 || total == 0) return SSFE_OK;
+    int rc = ensure(ctx, ctx->ws.misc, total * sizeof(float) + static_cast<size_t>(n) * 2 * sizeof(float) +
+                                           total * sizeof(int64_t));
+    if (rc) return rc;
+    float *scratch = static_cast<float *>(ctx->ws.misc.p);
+    float *stats = stats_dev ? stats_dev : scratch + total;
+    int64_t *tmp_bins = reinterpret_cast<int64_t *>(
+        reinterpret_cast<char *>(ctx->ws.misc.p) + (total * sizeof(float) + static_cast<size_t>(n) * 2 * sizeof(float) + 7) / 8 * 8);
+    int64_t *d_off = upload(ctx, frame_off_host, n + 1);
+    if (!d_off) return SSFE_ERR_NOMEM;
+    f0_stats_kernel<<<static_cast<unsigned>(grid_for(n, 64)), 64, 0, ctx->stream>>>(f0_dev, d_off, n, scratch, stats);
+    SSFE_LAUNCHED(ctx);
+    int64_t *use_bins = bins ? bins : (onehot ? tmp_bins : nullptr);
+    f0_norm_quant_kernel<<<static_cast<unsigned>(grid_for(total, 256)), 256, 0, ctx->stream>>>(
+        f0_dev, d_off, n, stats, total, f0_norm_dev, use_bins);
+    SSFE_LAUNCHED(ctx);
+    if (onehot) {
+        const int64_t work = total * 257;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>(grid_for(work, 256), 148LL * 64));
+        onehot_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(use_bins, total, 257, onehot);
+        SSFE_LAUNCHED(ctx);
+    }
+    return SSFE_OK;
+}
+}  // namespace ssfe
+
+extern "C" int ssfe_f0_normalize(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_offsets, int n_utts,
+                                 float *f0_norm_dev, float *stats_dev)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    if (!f0_dev || !frame_offsets || !f0_norm_dev || n_utts < 0)
+        return set_error(ctx, SSFE_ERR_INVALID, "ssfe_f0_normalize: null argument");
+    return f0_post_run(ctx, f0_dev, frame_offsets, n_utts, f0_norm_dev, stats_dev, nullptr, nullptr);
+}
+
+extern "C" int ssfe_speaker_normalization(ssfe_ctx *ctx, const void *f0_dev, int dtype,
+                                          const uint8_t *index_nonzero_dev, double mean_f0, double std_f0,
+                                          int64_t count, double *out_dev)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    if (count == 0) return SSFE_OK;
+    if (!f0_dev || !index_nonzero_dev || !out_dev)
+        return set_error(ctx, SSFE_ERR_INVALID, "ssfe_speaker_normalization: null argument");
+    const unsigned grid = static_cast<unsigned>(grid_for(count, 256));
+    if (dtype == SSFE_F32)
+        speaker_norm_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float *>(f0_dev),
+                                                                  index_nonzero_dev, mean_f0, std_f0, count, out_dev);
+    else if (dtype == SSFE_F64)
+        speaker_norm_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double *>(f0_dev),
+                                                                   index_nonzero_dev, mean_f0, std_f0, count, out_dev);
+    else
+        return set_error(ctx, SSFE_ERR_INVALID, "ssfe_speaker_normalization: dtype must be f32 or f64");
+    SSFE_LAUNCHED(ctx);
+    return SSFE_OK;
+}
+
+extern "C" int ssfe_quantize_f0(ssfe_ctx *ctx, const void *x_dev, int dtype, int64_t count, int num_bins,
+                                float *onehot_dev, int64_t *bins_dev, int check_range)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    if (count == 0) return SSFE_OK;
+    if (!x_dev || num_bins < 1) return set_error(ctx, SSFE_ERR_INVALID, "ssfe_quantize_f0: bad argument");
+    int rc = ensure(ctx, ctx->ws.misc, count * sizeof(int) + 64);
+    if (rc) return rc;
+    int *flag = static_cast<int *>(ctx->ws.misc.p);
+    int *bins32 = flag + 16;
+    SSFE_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    const unsigned grid = static_cast<unsigned>(grid_for(count, 256));
+    if (dtype == SSFE_F32)
+        quantize_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float *>(x_dev), count, num_bins,
+                                                              bins_dev, bins32, flag);
+    else if (dtype == SSFE_F64)
+        quantize_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double *>(x_dev), count, num_bins,
+                                                               bins_dev, bins32, flag);
+    else
+        return set_error(ctx, SSFE_ERR_INVALID, "ssfe_quantize_f0: dtype must be f32 or f64");
+    SSFE_LAUNCHED(ctx);
+    if (check_range) {
+        int h = 0;
+        SSFE_CUDA(ctx, cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h) return set_error(ctx, SSFE_ERR_RANGE, "quantize_f0: value outside [0, 1] (utils.py:52)");
+    }
+    if (onehot_dev) {
+        const int64_t work = count * (num_bins + 1);
+        const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(grid_for(work, 256), 148LL * 64));
+        onehot_kernel<int><<<g2, 256, 0, ctx->stream>>>(bins32, count, num_bins + 1, onehot_dev);
+        SSFE_LAUNCHED(ctx);
+    }
+    return SSFE_OK;
+}
+
+// ---- collator (data_loader.py:101-128) --------------------------------------------------------
+__global__ void collate_kernel(const float *__restrict__ mel, const float *__restrict__ f0n,
+                               const int64_t *__restrict__ frame_off, const int *__restrict__ utt,
+                               const int *__restrict__ left, const int *__restrict__ len_crop, int max_len_pad,
+                               float *__restrict__ melsp, float *__restrict__ pitch, float *__restrict__ onehot,
+                               int64_t *__restrict__ bins)
+{
+    const int item = blockIdx.y;
+    const int row = blockIdx.x;                 // padded frame index
+    const int tid = threadIdx.x;
+    const int u = utt[item];
+    const int len = len_crop[item];
+    const bool live = row < len;
+    const int64_t src = frame_off[u] + left[item] + row;
+    const int64_t dst = static_cast<int64_t>(item) * max_len_pad + row;
+    if (tid < kMels) {
+        float v = 0.0f;
+        if (live) v = fminf(fmaxf(mel[src * kMels + tid], 0.0f), 1.0f);   // np.clip(a, 0, 1), :113
+        melsp[dst * kMels + tid] = v;
+    }
+    const float p = live ? f0n[src] : kUnvoiced;                          // :116
+    if (tid == 0) pitch[dst] = p;
+    if (onehot || bins) {
+        bool bad = false;
+        const int b = static_cast<int>(quantize_value(static_cast<double>(p), 256, &bad));
+        if (bins && tid == 0) bins[dst] = b;
+        if (onehot)
+            for (int c = tid; c < 257; c += blockDim.x) onehot[dst * 257 + c] = (c == b) ? 1.0f : 0.0f;
+    }
+}
+
+extern "C" int ssfe_collate(ssfe_ctx *ctx, const float *mel_dev, const float *f0_norm_dev,
+                            const int64_t *frame_offsets, int n_items, const int32_t *utt, const int32_t *left,
+                            const int32_t *len_crop, int max_len_pad, float *melsp_dev, float *pitch_dev,
+                            float *onehot_dev, int64_t *bins_dev)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    if (n_items == 0) return SSFE_OK;
+    if (!mel_dev || !f0_norm_dev || !frame_offsets || !utt || !left || !len_crop || !melsp_dev || !pitch_dev ||
+        max_len_pad < 1)
+        return set_error(ctx, SSFE_ERR_INVALID, "ssfe_collate: bad argument");
+    int max_u = 0;
+    for (int i = 0; i < n_items; ++i) {
+        if (utt[i] < 0 || left[i] < 0 || len_crop[i] < 0 || len_crop[i] > max_len_pad)
+            return set_error(ctx, SSFE_ERR_INVALID, "ssfe_collate: item %d has a bad crop", i);
+        max_u = std::max(max_u, utt[i]);
+    }
+    for (int i = 0; i < n_items; ++i) {
+        const int64_t T = frame_offsets[utt[i] + 1] - frame_offsets[utt[i]];
+        if (left[i] + len_crop[i] > T)
+            return set_error(ctx, SSFE_ERR_INVALID, "ssfe_collate: crop of item %d exceeds utterance", i);
+    }
+    int64_t *d_off = upload(ctx, frame_offsets, max_u + 2);
+    int *d_utt = upload(ctx, utt, n_items), *d_left = upload(ctx, left, n_items),
+        *d_len = upload(ctx, len_crop, n_items);
+    if (!d_off || !d_utt || !d_left || !d_len) return SSFE_ERR_NOMEM;
+    dim3 grid(max_len_pad, n_items);
+    collate_kernel<<<grid, 96, 0, ctx->stream>>>(mel_dev, f0_norm_dev, d_off, d_utt, d_left, d_len, max_len_pad,
+                                                 melsp_dev, pitch_dev, onehot_dev, bins_dev);
+    SSFE_LAUNCHED(ctx);
+    return SSFE_OK;
+}

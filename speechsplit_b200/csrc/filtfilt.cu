@@ -1,0 +1,355 @@
+// filtfilt.cu - stages a0 + a1 (+ the deterministic part of a2).
+//
+// Replaces reference make_spect_f0.py:52-55:
+//     if L % 256 == 0: x = concat(x, [1e-06])
+//     y   = scipy.signal.filtfilt(b, a, x)           # b, a = butter_highpass(30, 16000, 5)
+//     wav = y * 0.96 + (prng.rand(L) - 0.5) * 1e-06
+// scipy's filtfilt (scipy/signal/_signaltools.py filtfilt/_validate_pad, _arraytools.odd_ext):
+// odd-extend by 18 samples, run the direct-form-II-transposed recurrence forward from
+// zi * ext[0], run it again over the reversed result from zi * y[-1], reverse, drop the pads.
+//
+// The order-5 recurrence is sequential in time.  It is evaluated as a chunked parallel scan:
+//   1. local : one thread per 256-sample chunk runs the recurrence from a ZERO state and keeps
+//              only the final state s_c (5 doubles);
+//   2. carry : per utterance, z_in[c+1] = A^256 z_in[c] + s_c.  The companion matrix A of this
+//              filter is violently non-normal (poles 0.988..0.996, max |A^k| ~ 1e8 at k ~ 256),
+//              so the carry is done in double-double arithmetic with A^256 computed in
+//              __float128 on the host (filt_consts.cpp); in plain fp64 the scan loses all digits;
+//   3. final : one thread per chunk re-runs the recurrence from its true z_in and writes outputs,
+//              with exactly scipy's operation order ((z[i+1] + x*b) - y*a, no FMA contraction).
+// The backward pass fuses the dither combine and scatters wav (f32) into the padded segment
+// layout the STFT kernel reads.  scipy's own sequential fp64 result carries ~2e-7 of low-frequency
+// round-off (measured against exact arithmetic); the scan agrees with it to that level.
+// filtfilt_mode 1 runs one thread per utterance (chunk = whole signal): a validation aid.
+#include "common.cuh"
+#include <algorithm>
+
+namespace ssfe {
+
+extern "C" void ssfe_filt_power_dd(const double *a6, int power, double *hi25, double *lo25);   // filt_consts.cpp
+
+constexpr int kChunk = 256;
+constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
+constexpr int kFiltThreads = 128;
+
+struct FiltConsts {
+    double b[6], a[6], zi[5];
+    double m_hi[25], m_lo[25];    // A^kChunk, row-major, double-double
+    double wav_scale, dither_scale;
+};
+
+struct FiltParams {
+    const void *x;                // input samples (pass 1) or nullptr
+    const double *y1;             // forward result over the extended signal (pass 2 input)
+    const int64_t *in_off;        // [n+1] raw input offsets
+    const int64_t *fix_off;       // [n+1] fixed (post-append) offsets
+    const int *chunk_off;         // [n+1] prefix of chunk counts
+    int n, n_chunks, chunk_len;
+    double *state;                // [n_chunks][5] zero-state finals, then overwritten by z_in
+    // outputs of the backward pass
+    double *y;
+    const double *dith;
+    float *wavp;
+    const int64_t *seg_off;
+    float *wav;
+    double *wav64;
+    double *y1_out;               // forward pass output (extended)
+};
+
+__constant__ FiltConsts c_filt;
+
+template <int DTYPE>
+__device__ __forceinline__ double load_sample(const void *x, int64_t i)
+{
+    if (DTYPE == SSFE_F32) return static_cast<double>(static_cast<const float *>(x)[i]);
+    if (DTYPE == SSFE_F64) return static_cast<const double *>(x)[i];
+    return static_cast<double>(static_cast<const short *>(x)[i]) * (1.0 / 32768.0);
+}
+
+// x'[n] of the fixed-length signal: the appended sample is 1e-06 (make_spect_f0.py:53)
+template <int DTYPE>
+__device__ __forceinline__ double fixed_sample(const void *x, int64_t base, int64_t L, int64_t n)
+{
+    return (n < L) ? load_sample<DTYPE>(x, base + n) : 1e-06;
+}
+
+// ext[j], j in [0, Lf + 36): scipy odd_ext(x, 18)
+template <int DTYPE>
+__device__ __forceinline__ double ext_sample(const void *x, int64_t base, int64_t L, int64_t Lf, int64_t j)
+{
+    if (j < kPadLen)
+        return __dsub_rn(2.0 * fixed_sample<DTYPE>(x, base, L, 0), fixed_sample<DTYPE>(x, base, L, kPadLen - j));
+    if (j < kPadLen + Lf) return fixed_sample<DTYPE>(x, base, L, j - kPadLen);
+    const int64_t k = j - kPadLen - Lf;
+    return __dsub_rn(2.0 * fixed_sample<DTYPE>(x, base, L, Lf - 1), fixed_sample<DTYPE>(x, base, L, Lf - 2 - k));
+}
+
+struct Df2t {
+    double z0, z1, z2, z3, z4;
+    __device__ __forceinline__ double step(double x)
+    {
+        const FiltConsts &c = c_filt;
+        const double y = __dadd_rn(z0, __dmul_rn(c.b[0], x));
+        z0 = __dsub_rn(__dadd_rn(z1, __dmul_rn(x, c.b[1])), __dmul_rn(y, c.a[1]));
+        z1 = __dsub_rn(__dadd_rn(z2, __dmul_rn(x, c.b[2])), __dmul_rn(y, c.a[2]));
+        z2 = __dsub_rn(__dadd_rn(z3, __dmul_rn(x, c.b[3])), __dmul_rn(y, c.a[3]));
+        z3 = __dsub_rn(__dadd_rn(z4, __dmul_rn(x, c.b[4])), __dmul_rn(y, c.a[4]));
+        z4 = __dsub_rn(__dmul_rn(x, c.b[5]), __dmul_rn(y, c.a[5]));
+        return y;
+    }
+};
+
+// PASS: 0 = forward over ext (input x), 1 = backward over reversed y1.
+// FINAL: false = zero-state local pass (writes final state), true = re-run from z_in, write outputs.
+template <int DTYPE, int PASS, bool FINAL>
+__global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltParams p)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_chunks) return;
+    const int u = find_segment(p.chunk_off, p.n, g);
+    const int c = g - p.chunk_off[u];
+    const int64_t L = p.in_off[u + 1] - p.in_off[u];
+    const int64_t fbase = p.fix_off[u];
+    const int64_t Lf = p.fix_off[u + 1] - fbase;
+    const int64_t M = Lf + 2 * kPadLen;
+    const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;   // extended-signal offset
+    const int64_t j0 = static_cast<int64_t>(c) * p.chunk_len;
+    const int64_t j1 = min(M, j0 + p.chunk_len);
+    const bool last_chunk = (j1 == M);
+    if (!FINAL && last_chunk) return;        // nobody consumes the carry out of the last chunk
+
+    Df2t f;
+    if (FINAL) {
+        const double *s = p.state + static_cast<int64_t>(g) * 5;
+        f.z0 = s[0]; f.z1 = s[1]; f.z2 = s[2]; f.z3 = s[3]; f.z4 = s[4];
+    } else {
+        f.z0 = f.z1 = f.z2 = f.z3 = f.z4 = 0.0;
+    }
+    const int64_t xbase = p.in_off[u];
+    const double *y1 = p.y1 + ebase;
+    for (int64_t j = j0; j < j1; ++j) {
+        double xin;
+        if (PASS == 0) xin = ext_sample<DTYPE>(p.x, xbase, L, Lf, j);
+        else xin = y1[M - 1 - j];
+        const double y = f.step(xin);
+        if (FINAL) {
+            if (PASS == 0) {
+                p.y1_out[ebase + j] = y;
+            } else {
+                const int64_t nidx = M - 1 - kPadLen - j;      // output sample index
+                if (nidx >= 0 && nidx < Lf) {
+                    if (p.y) p.y[fbase + nidx] = y;
+                    if (p.dith) {
+                        const double d = __dmul_rn(__dsub_rn(p.dith[fbase + nidx], 0.5), c_filt.dither_scale);
+                        const double w = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
+                        if (p.wav64) p.wav64[fbase + nidx] = w;
+                        const float wf = static_cast<float>(w);
+                        if (p.wav) p.wav[fbase + nidx] = wf;
+                        if (p.wavp) p.wavp[p.seg_off[u] + kHalfPad + nidx] = wf;
+                    }
+                }
+            }
+        }
+    }
+    if (!FINAL) {
+        double *s = p.state + static_cast<int64_t>(g) * 5;
+        s[0] = f.z0; s[1] = f.z1; s[2] = f.z2; s[3] = f.z3; s[4] = f.z4;
+    }
+}
+
+// ---- double-double helpers for the carry -------------------------------------------------------
+struct dd {
+    double hi, lo;
+};
+__device__ __forceinline__ dd dd_two_sum(double a, double b)
+{
+    const double s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    const double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+    return {s, e};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b)
+{
+    dd s = dd_two_sum(a.hi, b.hi);
+    const dd t = dd_two_sum(a.lo, b.lo);
+    s.lo = __dadd_rn(s.lo, t.hi);
+    s = dd_two_sum(s.hi, s.lo);           // (fast two-sum would do; keep the safe form)
+    s.lo = __dadd_rn(s.lo, t.lo);
+    return dd_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ dd dd_mul(dd a, dd b)
+{
+    const double p = __dmul_rn(a.hi, b.hi);
+    double e = __fma_rn(a.hi, b.hi, -p);
+    e = __fma_rn(a.hi, b.lo, e);
+    e = __fma_rn(a.lo, b.hi, e);
+    return dd_two_sum(p, e);
+}
+
+// one thread per utterance: turn the zero-state finals into true chunk-entry states
+template <int DTYPE, int PASS>
+__global__ void filt_carry_kernel(const FiltParams p)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.n) return;
+    const int c0 = p.chunk_off[u], nc = p.chunk_off[u + 1] - c0;
+    const int64_t L = p.in_off[u + 1] - p.in_off[u];
+    const int64_t fbase = p.fix_off[u];
+    const int64_t Lf = p.fix_off[u + 1] - fbase;
+    const int64_t M = Lf + 2 * kPadLen;
+    const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
+    double x0;
+    if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
+    else x0 = p.y1[ebase + M - 1];
+    dd z[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z[i] = {__dmul_rn(c_filt.zi[i], x0), 0.0};
+    for (int c = 0; c < nc; ++c) {
+        double *s = p.state + static_cast<int64_t>(c0 + c) * 5;
+        double sc[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            sc[i] = s[i];
+            s[i] = z[i].hi;                       // z_in of this chunk (hi + lo rounds to hi)
+        }
+        if (c + 1 == nc) break;
+        dd zn[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            dd acc = {sc[i], 0.0};
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const dd m = {c_filt.m_hi[i * 5 + k], c_filt.m_lo[i * 5 + k]};
+                acc = dd_add(acc, dd_mul(m, z[k]));
+            }
+            zn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) z[i] = zn[i];
+    }
+}
+
+// reflect edges of the padded segments once the interior is written (np.pad 'reflect', utils.py:20)
+__global__ void reflect_edges_kernel(float *__restrict__ wavp, const int64_t *__restrict__ seg_off,
+                                     const int64_t *__restrict__ fix_off, int n)
+{
+    const int u = blockIdx.x;
+    if (u >= n) return;
+    const int64_t Lf = fix_off[u + 1] - fix_off[u];
+    float *seg = wavp + seg_off[u];
+    const int64_t period = (Lf > 1) ? 2 * (Lf - 1) : 1;
+    for (int t = threadIdx.x; t < 2 * kHalfPad; t += blockDim.x) {
+        const int64_t j = (t < kHalfPad) ? t : Lf + t;          // position in the padded segment
+        int64_t m = j - kHalfPad;
+        m %= period;
+        if (m < 0) m += period;
+        if (m >= Lf) m = period - m;
+        seg[j] = seg[kHalfPad + m];
+    }
+}
+
+int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, const int64_t *fix_off_dev, int n)
+{
+    if (n == 0) return SSFE_OK;
+    reflect_edges_kernel<<<n, 256, 0, ctx->stream>>>(wavp, seg_off_dev, fix_off_dev, n);
+    SSFE_LAUNCHED(ctx);
+    return SSFE_OK;
+}
+
+template <int DTYPE>
+static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential)
+{
+    const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
+    const unsigned gu = (p.n + 63) / 64;
+    cudaStream_t st = ctx->stream;
+    if (!sequential) {
+        filt_chunk_kernel<DTYPE, 0, false><<<gc, kFiltThreads, 0, st>>>(p);
+        SSFE_LAUNCHED(ctx);
+    }
+    filt_carry_kernel<DTYPE, 0><<<gu, 64, 0, st>>>(p);
+    SSFE_LAUNCHED(ctx);
+    filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
+    SSFE_LAUNCHED(ctx);
+    p.y1 = p.y1_out;
+    if (!sequential) {
+        filt_chunk_kernel<DTYPE, 1, false><<<gc, kFiltThreads, 0, st>>>(p);
+        SSFE_LAUNCHED(ctx);
+    }
+    filt_carry_kernel<DTYPE, 1><<<gu, 64, 0, st>>>(p);
+    SSFE_LAUNCHED(ctx);
+    filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
+    SSFE_LAUNCHED(ctx);
+    return SSFE_OK;
+}
+
+int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_off_host,
+                 const int64_t *fix_off_host, int n, const FiltOut &out)
+{
+    if (n == 0) return SSFE_OK;
+    const bool sequential = ctx->cfg.filtfilt_mode == 1;
+    std::vector<int> chunk_off(n + 1);
+    int64_t chunks = 0, max_m = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t Lf = fix_off_host[i + 1] - fix_off_host[i];
+        if (Lf <= kPadLen)
+            return set_error(ctx, SSFE_ERR_TOO_SHORT,
+                             "utterance %d: the length of the input vector x must be greater than padlen, which is 18", i);
+        const int64_t M = Lf + 2 * kPadLen;
+        max_m = std::max(max_m, M);
+        chunk_off[i] = static_cast<int>(chunks);
+        chunks += sequential ? 1 : (M + kChunk - 1) / kChunk;
+        if (chunks > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (chunks)");
+    }
+    chunk_off[n] = static_cast<int>(chunks);
+    const int64_t ext_total = fix_off_host[n] + static_cast<int64_t>(n) * 2 * kPadLen;
+    int rc = ensure(ctx, ctx->ws.y1, ext_total * sizeof(double));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->ws.carry, chunks * 5 * sizeof(double));
+    if (rc) return rc;
+
+    FiltParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = x_dev;
+    p.y1 = nullptr;
+    p.in_off = upload(ctx, in_off_host, n + 1);
+    p.fix_off = upload(ctx, fix_off_host, n + 1);
+    p.chunk_off = upload(ctx, chunk_off.data(), n + 1);
+    if (!p.in_off || !p.fix_off || !p.chunk_off) return SSFE_ERR_NOMEM;
+    p.n = n;
+    p.n_chunks = static_cast<int>(chunks);
+    p.chunk_len = sequential ? static_cast<int>(std::min<int64_t>(max_m, 0x7fffffff)) : kChunk;
+    p.state = static_cast<double *>(ctx->ws.carry.p);
+    p.y = out.y;
+    p.dith = out.dith;
+    p.wavp = out.wavp;
+    p.seg_off = out.seg_off_dev;
+    p.wav = out.wav;
+    p.wav64 = out.wav64;
+    p.y1_out = static_cast<double *>(ctx->ws.y1.p);
+    switch (dtype) {
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential);
+    default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
+    }
+}
+
+int init_filtfilt(ssfe_ctx *ctx)
+{
+    FiltConsts c;
+    memset(&c, 0, sizeof(c));
+    for (int i = 0; i < 6; ++i) {
+        c.b[i] = ctx->cfg.b[i] / ctx->cfg.a[0];      // scipy normalises by a[0] (== 1 here)
+        c.a[i] = ctx->cfg.a[i] / ctx->cfg.a[0];
+    }
+    for (int i = 0; i < 5; ++i) c.zi[i] = ctx->cfg.zi[i];
+    ssfe_filt_power_dd(c.a, kChunk, c.m_hi, c.m_lo);
+    c.wav_scale = ctx->cfg.wav_scale;
+    c.dither_scale = ctx->cfg.dither_scale;
+    SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_filt, &c, sizeof(c)));
+    return SSFE_OK;
+}
+
+void free_filtfilt(ssfe_ctx *) {}
+
+}  // namespace ssfe

@@ -1,0 +1,153 @@
+// mt19937.cu - the per-speaker dither stream (stage a2, random part).
+//
+// Replaces numpy.random.RandomState(int(subdir[1:])).rand(L) at reference make_spect_f0.py:47,55.
+// RandomState(seed) is MT19937 seeded with init_genrand (Knuth LCG 1812433253); rand() returns
+// ((a >> 5) * 2^26 + (b >> 6)) / 2^53 from two successive tempered 32-bit outputs.  A speaker's
+// stream continues across its files in sorted order, so utterance k starts `skip` doubles in.
+//
+// One CTA per distinct seed walks the stream block by block (624 words): the twist of a block
+// has three dependent sub-steps of 227 / 227 / 170 independent words, separated by
+// __syncthreads(); 312 doubles per block are tempered and written coalesced to every request of
+// that seed that overlaps the block.  Streams are independent, so seeds run on different SMs.
+#include "common.cuh"
+#include <algorithm>
+#include <numeric>
+
+namespace ssfe {
+
+constexpr int kMtN = 624, kMtM = 397;
+constexpr int kMtThreads = 320;
+
+struct RandJob {
+    uint32_t seed;
+    int first_req, n_req;
+    int pad;
+};
+struct RandReq {
+    uint64_t skip;       // first double of the stream this request wants
+    int64_t count;       // doubles
+    int64_t out_off;     // into the output array
+};
+
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
+{
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+__global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__restrict__ jobs,
+                                                             const RandReq *__restrict__ reqs,
+                                                             double *__restrict__ out)
+{
+    __shared__ uint32_t s_mt[2][kMtN];
+    const RandJob job = jobs[blockIdx.x];
+    const RandReq *rq = reqs + job.first_req;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {   // init_genrand(seed): a 624-step serial LCG, once per stream
+        uint32_t v = job.seed;
+        s_mt[0][0] = v;
+        for (int i = 1; i < kMtN; ++i) {
+            v = 1812433253u * (v ^ (v >> 30)) + static_cast<uint32_t>(i);
+            s_mt[0][i] = v;
+        }
+    }
+    __syncthreads();
+
+    const uint64_t last_double = rq[job.n_req - 1].skip + static_cast<uint64_t>(rq[job.n_req - 1].count);
+    const uint64_t n_blocks = (last_double + 311) / 312;   // blocks of 312 doubles to generate
+    int r0 = 0;                                            // first request not entirely before this block
+    int cur = 0;
+    for (uint64_t blk = 0; blk < n_blocks; ++blk) {
+        const uint32_t *o = s_mt[cur];
+        uint32_t *nw = s_mt[cur ^ 1];
+        if (tid < 227) nw[tid] = o[tid + kMtM] ^ mt_mix(o[tid], o[tid + 1]);
+        __syncthreads();
+        if (tid < 227) nw[tid + 227] = nw[tid] ^ mt_mix(o[tid + 227], o[tid + 228]);
+        __syncthreads();
+        if (tid < 169) nw[tid + 454] = nw[tid + 227] ^ mt_mix(o[tid + 454], o[tid + 455]);
+        else if (tid == 169) nw[623] = nw[396] ^ mt_mix(o[623], nw[0]);
+        __syncthreads();
+        cur ^= 1;
+
+        const uint64_t d0 = blk * 312;                     // first double of this block
+        while (r0 < job.n_req && rq[r0].skip + static_cast<uint64_t>(rq[r0].count) <= d0) ++r0;
+        if (r0 < job.n_req && rq[r0].skip < d0 + 312 && tid < 312) {
+            const uint64_t d = d0 + tid;
+            int r = r0;
+            while (r < job.n_req && rq[r].skip + static_cast<uint64_t>(rq[r].count) <= d) ++r;
+            if (r < job.n_req && d >= rq[r].skip) {
+                const uint32_t a = mt_temper(nw[2 * tid]) >> 5, b = mt_temper(nw[2 * tid + 1]) >> 6;
+                const double u = (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) / 9007199254740992.0;
+                out[rq[r].out_off + static_cast<int64_t>(d - rq[r].skip)] = u;
+            }
+        }
+        // no barrier needed here: the next twist writes the buffer that was last *read* before
+        // the third barrier above, and reads the buffer the output phase is reading.
+    }
+}
+
+int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off, int n,
+             double *u_dev)
+{
+    if (n == 0) return SSFE_OK;
+    // group requests by seed, each group ordered by stream position
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (seeds[a] != seeds[b]) return seeds[a] < seeds[b];
+        return skip[a] < skip[b];
+    });
+    std::vector<RandJob> jobs;
+    std::vector<RandReq> reqs;
+    reqs.reserve(n);
+    for (int k = 0; k < n; ++k) {
+        const int i = order[k];
+        const int64_t cnt = out_off[i + 1] - out_off[i];
+        if (cnt <= 0) continue;
+        if (jobs.empty() || jobs.back().seed != seeds[i]) {
+            RandJob j;
+            j.seed = seeds[i];
+            j.first_req = static_cast<int>(reqs.size());
+            j.n_req = 0;
+            j.pad = 0;
+            jobs.push_back(j);
+        } else {
+            const RandReq &prev = reqs.back();
+            if (skip[i] < prev.skip + static_cast<uint64_t>(prev.count))
+                return set_error(ctx, SSFE_ERR_INVALID, "ssfe_rand: overlapping stream ranges for seed %u", seeds[i]);
+        }
+        RandReq r;
+        r.skip = skip[i];
+        r.count = cnt;
+        r.out_off = out_off[i];
+        reqs.push_back(r);
+        jobs.back().n_req++;
+    }
+    if (jobs.empty()) return SSFE_OK;
+    RandJob *d_jobs = upload(ctx, jobs.data(), jobs.size());
+    RandReq *d_reqs = upload(ctx, reqs.data(), reqs.size());
+    if (!d_jobs || !d_reqs) return SSFE_ERR_NOMEM;
+    mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, ctx->stream>>>(d_jobs, d_reqs, u_dev);
+    SSFE_LAUNCHED(ctx);
+    return SSFE_OK;
+}
+
+}  // namespace ssfe
+
+extern "C" int ssfe_rand(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_offsets,
+                         int n_utts, double *u_dev)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    if (n_utts < 0 || (n_utts > 0 && (!seeds || !skip || !out_offsets || !u_dev)))
+        return ssfe::set_error(ctx, SSFE_ERR_INVALID, "ssfe_rand: null argument");
+    return ssfe::rand_run(ctx, seeds, skip, out_offsets, n_utts, u_dev);
+}
