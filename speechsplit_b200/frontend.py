@@ -118,7 +118,11 @@ class FrontEnd:
             _raise(rc, self.lib.ssfe_last_error(self._h).decode())
 
     def _bind_stream(self):
-        self._check(self.lib.ssfe_set_stream(self._h, L.vp(torch.cuda.current_stream(self.device).cuda_stream)))
+        """Enqueue on torch's current stream so results are ordered with the caller's tensors.
+        torch's default stream has handle 0, which the C ABI reads as "use the context's own
+        stream"; pass CUDA's explicit legacy-default handle (cudaStreamLegacy == 0x1) instead."""
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.ssfe_set_stream(self._h, L.vp(h if h else 1)))
 
     def _dev(self, t, dtype=None):
         if isinstance(t, np.ndarray):
