@@ -122,6 +122,13 @@ int ssfe_stft_mel_db(ssfe_ctx *ctx, const float *wav_dev, const int64_t *offsets
 int ssfe_rapt(ssfe_ctx *ctx, const float *wav_dev, const int64_t *offsets, int n_utts,
               const float *f0_lo, const float *f0_hi, float *f0_dev);
 
+/* Diagnostics for the parity tests: the per-frame records the most recent ssfe_rapt / ssfe_extract
+ * left behind (frames RAPT analysed, batch order): candidate count incl. the unvoiced one, lags
+ * (-1 = unvoiced), local costs, the F0 each candidate would emit, stationarity, rms ratio.  Any
+ * pointer may be NULL.  Synchronous; returns the number of frames copied or a negative status. */
+int64_t ssfe_rapt_dump(ssfe_ctx *ctx, int64_t max_frames, uint8_t *ncand, int16_t *loc /* [f,20] */,
+                       float *mp /* [f,20] */, float *f0cand /* [f,20] */, float *stat, float *rms_ratio);
+
 /* (a7+a8) make_spect_f0.py:65-67 + utils.speaker_normalization (utils.py:35-42): per-utterance
  * float32 mean / std (ddof 0, numpy pairwise order) of the voiced log-F0, then
  * ((f0-mean)/std/4 clipped to [-1,1] + 1)/2 in float64, stored float32; unvoiced stays -1e10.

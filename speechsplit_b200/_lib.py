@@ -59,6 +59,7 @@ SIGNATURES = {
     "ssfe_stft_mag": (ctypes.c_int, [vp, vp, c_i64p, ctypes.c_int, vp]),
     "ssfe_stft_mel_db": (ctypes.c_int, [vp, vp, c_i64p, ctypes.c_int, vp]),
     "ssfe_rapt": (ctypes.c_int, [vp, vp, c_i64p, ctypes.c_int, c_f32p, c_f32p, vp]),
+    "ssfe_rapt_dump": (ctypes.c_int64, [vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp]),
     "ssfe_f0_normalize": (ctypes.c_int, [vp, vp, c_i64p, ctypes.c_int, vp, vp]),
     "ssfe_speaker_normalization": (ctypes.c_int, [vp, vp, ctypes.c_int, vp, ctypes.c_double, ctypes.c_double,
                                                   ctypes.c_int64, vp]),

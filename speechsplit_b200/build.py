@@ -15,6 +15,8 @@ OUT = os.path.join(PKG, "libssfe.so")
 OBJ = os.path.join(PKG, "_obj")
 CU = ["api.cu", "stft_mel.cu", "filtfilt.cu", "mt19937.cu", "f0_post.cu", "rapt.cu"]
 CPP = ["filt_consts.cpp"]
+# RAPT reproduces the original's float evaluation order; fused multiply-adds would change it
+EXTRA = {"rapt.cu": ["--fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -37,7 +39,8 @@ def build(force=False, verbose=False):
         src, obj = os.path.join(CSRC, f), os.path.join(OBJ, f + ".o")
         objs.append(obj)
         if force or _newer(src, obj, headers):
-            r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+            r = subprocess.run([nvcc] + NVCC_FLAGS + EXTRA.get(f, []) + ["-c", src, "-o", obj],
+                               capture_output=True, text=True)
             logs.append((f, r.stderr))
             if r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)

@@ -1,12 +1,838 @@
-// rapt.cu - placeholder until the RAPT kernels land (stage a6).
+// rapt.cu - RAPT pitch tracking (stage a6) for ragged batches.
+//
+// Replaces reference make_spect_f0.py:64
+//     f0_rapt = pysptk.sptk.rapt(wav.astype(np.float32)*32768, 16000, 256, min=lo, max=hi, otype=2)
+// i.e. SPTK's Snack/ESPS get_f0 (D. Talkin's RAPT) with the parameters rapt() installs.  pysptk is
+// a third-party dependency that is not vendored in the reference; the algorithm is restated from
+// its published description (see oracle/rapt_ref.c, which is this file's CPU checker).
+//
+// The original is a streaming C program (0.2 s reads, float accumulators, static buffers).  Voicing
+// decisions are discontinuous in the arithmetic, so this file keeps its evaluation ORDER - every
+// running sum is formed by one thread, left to right, in the original's precision mix; the file is
+// compiled with --fmad=false - and re-expresses the streaming structure in closed form per frame:
+//   K1 rapt_decimate   thread per 2 kHz sample: 81-tap symmetric FIR, every 8th output        (A1)
+//   K2 rapt_cand       warp per frame: coarse NCCF on the 2 kHz stream, peak picking, parabolic
+//                      refinement, fine NCCF (+-3 lags around each coarse peak), peak picking,
+//                      local costs and the refined F0 each candidate would emit          (A2-A5)
+//   K3 rapt_stat       warp per frame: two 30 ms LPC analyses (order 18, Hanning, pre-emphasis),
+//                      Itakura distance -> stationarity, rms ratio                          (A6)
+//   K4 rapt_dp         warp per utterance: Viterbi over <= 20 candidates per frame with warp
+//                      shuffles (lane = current candidate), the original's commit-on-convergence
+//                      back-tracking at every 0.2 s read boundary, log(F0) output          (A7-A8)
+// K1-K3 are frame parallel (the bulk of the work); only K4 is sequential in time.
 #include "common.cuh"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
 namespace ssfe {
-struct RaptTables { int dummy; };
-int init_rapt(ssfe_ctx *) { return SSFE_OK; }
-void free_rapt(ssfe_ctx *) {}
-int rapt_run(ssfe_ctx *ctx, const float *, const int64_t *, const int64_t *, const int64_t *, int,
-             const float *, const float *, float *)
+
+constexpr int kCMax = 20;          // n_cands
+constexpr int kDec = 8;            // (int)(fs / 2000)
+constexpr int kWin = 120;          // round(0.0075 * fs)
+constexpr int kNco = 81;           // decimator taps
+constexpr int kStatW = 480, kStatGap = 320, kLpcOrd = 18;
+constexpr int kRing = 128;         // back-pointer history per utterance (>= DP_LIMIT + one read)
+constexpr int kCcMax = 288;        // nlags (<= 257) + slack
+constexpr int kPkMax = 264;
+
+struct RaptCfg {
+    int start, stop, nlags, ncomp, pad, F, buff_size, sdstep;
+    int decstart, decnlags, decsize, n_el;
+    float lagwt, lag_wt;
+    int table_off, pad0;
+};
+
+struct RaptConsts {
+    RaptCfg cfg[2];
+    float co[kNco];
+    float cand_thresh, tcost, tfact_a, tfact_s, vbias, ffact, preemp;
+    int size_frame_hist, size_frame_out;
+};
+
+struct RaptUtt {
+    long long wav_off, out_off, fr_off, ds_off;
+    int L, cfg, n_out, n_fr, n_ds, R_last, nl, pad;
+};
+
+struct RaptTables {
+    float *d_ferr = nullptr;       // voiced->voiced transition cost [cfg][lag1][lag2]
+    float *d_w479 = nullptr, *d_w480 = nullptr;
+    RaptConsts host;
+    // where the last rapt_run left its per-frame records (ssfe_rapt_dump)
+    long long last_fr = 0;
+    const unsigned char *last_ncand = nullptr;
+    const short *last_loc = nullptr;
+    const float *last_mp = nullptr, *last_f0c = nullptr, *last_sta = nullptr, *last_rr = nullptr;
+};
+
+__constant__ RaptConsts c_rapt;
+
+struct RaptParams {
+    const float *wav;
+    const RaptUtt *utts;
+    const long long *fr_offs;      // [n+1]
+    const long long *ds_offs;      // [n+1]
+    int n;
+    long long total_fr, total_ds;
+    float *ds;
+    // per analysed frame
+    unsigned char *ncand;          // incl. the unvoiced candidate
+    short *loc;                    // [fr][20]
+    float *mp;                     // [fr][20] local cost
+    float *f0c;                    // [fr][20] F0 (Hz) the candidate would emit, 0 = unvoiced
+    float *sta, *rr;
+    const float *ferr;
+    const float *w479, *w480;
+    float *out;                    // log-F0
+};
+
+// ---- K1 ------------------------------------------------------------------------------------
+__global__ void rapt_decimate_kernel(const RaptParams p)
 {
-    return set_error(ctx, SSFE_ERR_INVALID, "RAPT kernels not built yet");
+    const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (gid >= p.total_ds) return;
+    const int u = find_segment(p.ds_offs, p.n, gid);
+    const RaptUtt ut = p.utts[u];
+    const int m = static_cast<int>(gid - ut.ds_off);
+    const float *x = p.wav + ut.wav_off;
+    float sum = 0.0f;
+#pragma unroll 9
+    for (int j = 0; j < kNco; ++j) {
+        const int idx = kDec * m + j - (kNco / 2);
+        const float v = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+        sum += c_rapt.co[j] * v;
+    }
+    p.ds[gid] = static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
 }
+
+// ---- warp helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// peaks of correl[0..nl) above cand_thresh*maxval, in ascending lag order (get_cand)
+__device__ __forceinline__ int pick_candidates(const float *cc, int nl, int firstlag, float maxval,
+                                               float *peaks, int *locs, int lane)
+{
+    const float clip = c_rapt.cand_thresh * maxval;
+    const int lastl = nl - 2;
+    int count = 0;
+    for (int base = 1; base < lastl; base += 32) {
+        const int i = base + lane;
+        bool ok = false;
+        float q = 0.0f;
+        if (i < lastl) {
+            q = cc[i];
+            ok = (q > clip) && (q >= cc[i + 1]) && (q >= cc[i - 1]);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (ok && pos < kPkMax) {
+            peaks[pos] = q;
+            locs[pos] = i + firstlag;
+        }
+        count += __popc(mask);
+    }
+    __syncwarp();
+    return min(count, kPkMax);
+}
+
+// keep the n_cands-1 largest, by the original's partial bubble pass (order matters downstream)
+__device__ __forceinline__ int prune_candidates(float *peaks, int *locs, int ncand, int lane)
+{
+    if (ncand < kCMax) return ncand;
+    if (lane == 0) {
+        for (int outer = 0; outer < kCMax - 1; ++outer) {
+            int idx = ncand - 1;
+            for (int inner = ncand - 1 - outer; inner-- > 0; --idx) {
+                const float sm = peaks[idx];
+                if (sm > peaks[idx - 1]) {
+                    const int lt = locs[idx];
+                    peaks[idx] = peaks[idx - 1];
+                    peaks[idx - 1] = sm;
+                    locs[idx] = locs[idx - 1];
+                    locs[idx - 1] = lt;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return kCMax - 1;
+}
+
+// ---- K2 ------------------------------------------------------------------------------------
+constexpr int kCandWarps = 4;
+
+__global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p)
+{
+    __shared__ float s_db[kCandWarps][448];
+    __shared__ float s_cc[kCandWarps][kCcMax];
+    __shared__ float s_val[kCandWarps][kCMax * 7 + 4];
+    __shared__ float s_pk[kCandWarps][kPkMax];
+    __shared__ int s_lc[kCandWarps][kPkMax];
+    __shared__ int s_st[kCandWarps][kCMax];
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long gf = blockIdx.x * static_cast<long long>(kCandWarps) + w;
+    if (gf >= p.total_fr) return;
+    float *db = s_db[w], *cc = s_cc[w], *val = s_val[w], *pk = s_pk[w];
+    int *lc = s_lc[w], *stc = s_st[w];
+
+    const int u = find_segment(p.fr_offs, p.n, gf);
+    const RaptUtt ut = p.utts[u];
+    const RaptCfg &cf = c_rapt.cfg[ut.cfg];
+    const int g = static_cast<int>(gf - ut.fr_off);
+    int r, i, nfr_r;
+    const int full = ut.R_last * cf.F;
+    if (g < full) { r = g / cf.F; i = g - r * cf.F; nfr_r = cf.F; }
+    else { r = ut.R_last; i = g - full; nfr_r = ut.nl; }
+    const bool flushed = (r == ut.R_last) && (r > 0);     // last read of several: the FIR was flushed
+    const int samsds = ((nfr_r - 1) * kHop + cf.ncomp) / kDec;
+    const float *x = p.wav + ut.wav_off;
+    const float *ds = p.ds + ut.ds_off + static_cast<long long>(r) * (cf.sdstep / kDec);
+
+    // -- coarse stage on the 2 kHz stream ---------------------------------------------------------
+    for (int t = lane; t < cf.n_el; t += 32) {
+        const int q = (kHop / kDec) * i + t;
+        float v = 0.0f;
+        if (q < samsds) {
+            v = ds[q];
+        } else if (flushed) {
+            // samples the original produced while flushing the filter with zeros: output e of the
+            // flush sees its last 8e taps zeroed
+            const int e = q - samsds;
+            if (e == 0) {
+                v = ds[q];
+            } else {
+                const int base = r * cf.sdstep + kDec * q - (kNco / 2);
+                float sum = 0.0f;
+                for (int j = 0; j < kNco - kDec * e; ++j) {
+                    const int idx = base + j;
+                    const float xv = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+                    sum += c_rapt.co[j] * xv;
+                }
+                v = static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
+            }
+        }
+        db[t] = v;
+    }
+    __syncwarp();
+    float maxval = 0.0f;
+    int ncand = 0;
+    {
+        const int size = cf.decsize, start = cf.decstart, nlags = cf.decnlags;
+        float engr = 0.0f;
+        for (int j = 0; j < size; ++j) engr += db[j];
+        engr /= size;
+        __syncwarp();
+        for (int t = lane; t < cf.n_el; t += 32) db[t] = db[t] - engr;
+        __syncwarp();
+        float sum = 0.0f;
+        for (int j = 0; j < size; ++j) { const float st = db[j]; sum += st * st; }
+        engr = sum;
+        float t0 = 0.0f, t1 = 0.0f;
+        if (engr > 0.0f) {
+            sum = 0.0f;
+            for (int j = 0; j < size; ++j) { const float st = db[start + j]; sum += st * st; }
+            double engc = sum;
+            float dot0 = 0.0f, dot1 = 0.0f;
+            if (lane < nlags)
+                for (int j = 0; j < size; ++j) dot0 += db[j] * db[lane + start + j];
+            if (lane + 32 < nlags)
+                for (int j = 0; j < size; ++j) dot1 += db[j] * db[lane + 32 + start + j];
+            for (int k = 0; k < nlags; ++k) {
+                const double den = sqrt(engc * engr);
+                if (k == lane) t0 = dot0 / den;
+                if (k == lane + 32) t1 = dot1 / den;
+                const float a0 = db[k + start], az = db[k + start + size];
+                engc -= static_cast<double>(a0 * a0);
+                if ((engc += static_cast<double>(az * az)) < 1.0) engc = 1.0;
+            }
+        }
+        if (lane < nlags) cc[lane] = t0;
+        if (lane + 32 < nlags) cc[lane + 32] = t1;
+        maxval = warp_max(fmaxf(fmaxf(t0, t1), 0.0f));
+        __syncwarp();
+        ncand = pick_candidates(cc, nlags, start, maxval, pk, lc, lane);
+        // parabolic refinement to full-rate lags
+        const float lag_wt = cf.lag_wt;
+        for (int c = lane; c < ncand; c += 32) {
+            const float *y = cc + (lc[c] - start - 1);
+            float xp, yp;
+            const float a = static_cast<float>((y[2] - y[1]) + (.5 * (y[0] - y[2])));
+            if (fabs(a) > .000001) {
+                const float cq = static_cast<float>((y[0] - y[2]) / (4.0 * a));
+                xp = cq;
+                yp = y[1] - (a * cq * cq);
+            } else {
+                xp = 0.0f;
+                yp = y[1];
+            }
+            const int l2 = (lc[c] * kDec) + static_cast<int>(0.5 + (xp * kDec));
+            lc[c] = l2;
+            pk[c] = yp * (1.0 - (lag_wt * l2));
+        }
+        __syncwarp();
+        ncand = prune_candidates(pk, lc, ncand, lane);
+    }
+
+    // -- fine stage on the full-rate signal ---------------------------------------------------------
+    {
+        const int start0 = cf.start, nlags0 = cf.nlags, total = cf.ncomp;   // size + nlags0 + start0
+        const float *fx = x + static_cast<long long>(g) * kHop;
+        for (int t = lane; t < total; t += 32) db[t] = fx[t] * 32768.0f;
+        for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;
+        __syncwarp();
+        float engr = 0.0f;
+        for (int j = 0; j < kWin; ++j) engr += db[j];
+        engr /= kWin;
+        __syncwarp();
+        for (int t = lane; t < total; t += 32) db[t] = db[t] - engr;
+        __syncwarp();
+        float sum = 0.0f;
+        for (int j = 0; j < kWin; ++j) { const float st = db[j]; sum += st * st; }
+        engr = sum;
+        maxval = 0.0f;
+        if (engr > 0.0f) {
+            if (lane < ncand) {
+                int st = lc[lane] - 3;
+                if (st < start0) st = start0;
+                stc[lane] = st;
+            }
+            __syncwarp();
+            for (int wk = lane; wk < ncand * 7; wk += 32) {
+                const int c = wk / 7, t = wk - 7 * c;
+                const float *dsp = db + stc[c] + t;
+                float dot = 0.0f;
+                for (int j = 0; j < kWin; ++j) dot += db[j] * dsp[j];
+                val[wk] = dot;
+            }
+            __syncwarp();
+            if (lane < ncand) {
+                const int st = stc[lane];
+                float s2 = 0.0f;
+                for (int j = 0; j < kWin; ++j) { const float q = db[st + j]; s2 += q * q; }
+                double engc = s2;
+                for (int t = 0; t < 7; ++t) {
+                    if (engc < 1.0) engc = 1.0;
+                    const float dot = val[lane * 7 + t];
+                    val[lane * 7 + t] = static_cast<float>(dot / sqrt(10000.0 + (engc * engr)));
+                    const float a0 = db[st + t], az = db[st + t + kWin];
+                    engc -= static_cast<double>(a0 * a0);
+                    engc += static_cast<double>(az * az);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {   // windows are written in candidate order; later ones overwrite
+                float amax = 0.0f;
+                for (int c = 0; c < ncand; ++c) {
+                    const int o = stc[c] - start0;
+                    for (int t = 0; t < 7; ++t) {
+                        const float v = val[c * 7 + t];
+                        if (o + t < kCcMax) cc[o + t] = v;
+                        if (v > amax) amax = v;
+                    }
+                }
+                val[0] = amax;
+            }
+            __syncwarp();
+            maxval = val[0];
+        }
+        __syncwarp();
+        ncand = pick_candidates(cc, nlags0, start0, maxval, pk, lc, lane);
+        ncand = prune_candidates(pk, lc, ncand, lane);
+
+        // local costs (A5) and the value each candidate would emit (A8)
+        const float lagwt = cf.lagwt;
+        short *oloc = p.loc + gf * kCMax;
+        float *omp = p.mp + gf * kCMax, *of0 = p.f0c + gf * kCMax;
+        if (lane < ncand) {
+            const int loc1 = lc[lane];
+            const float pv = pk[lane];
+            float ftemp = 1.0 - (static_cast<float>(loc1) * lagwt);
+            omp[lane] = 1.0 - (pv * ftemp);
+            oloc[lane] = static_cast<short>(loc1);
+            ftemp = loc1;
+            if (loc1 > cf.start && loc1 < cf.stop) {
+                const int jj = loc1 - cf.start;
+                const float cormax = cc[jj], cprev = cc[jj + 1], cnext = cc[jj - 1];
+                const float den = (2.0 * (cprev + cnext - (2.0 * cormax)));
+                if (fabs(den) > 0.000001)
+                    ftemp += 2.0 - ((((5.0 * cprev) + (3.0 * cnext) - (8.0 * cormax)) / den));
+            }
+            of0[lane] = 16000.0 / ftemp;
+        } else if (lane == ncand) {
+            oloc[lane] = -1;
+            omp[lane] = c_rapt.vbias + maxval;
+            of0[lane] = 0.0f;
+        } else if (lane < kCMax) {
+            oloc[lane] = -1;
+            omp[lane] = 0.0f;
+            of0[lane] = 0.0f;
+        }
+        if (lane == 0) p.ncand[gf] = static_cast<unsigned char>(ncand + 1);
+    }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------
+// Levinson-Durbin on all lanes redundantly, fully unrolled so a[] and b[] stay in registers
+__device__ __forceinline__ void durbin18(const float *r, float *a_out, float *err)
+{
+    float a[kLpcOrd], b[kLpcOrd], k;
+    float e = r[0];
+    k = -r[1] / e;
+    a[0] = k;
+    e *= (1. - k * k);
+#pragma unroll
+    for (int i = 1; i < kLpcOrd; ++i) {
+        float s = 0;
+#pragma unroll
+        for (int j = 0; j < i; ++j) s -= a[j] * r[i - j];
+        k = (s - r[i + 1]) / e;
+        a[i] = k;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) b[j] = a[j];
+#pragma unroll
+        for (int j = 0; j < i; ++j) a[j] += k * b[i - j - 1];
+        e *= (1. - (k * k));
+    }
+#pragma unroll
+    for (int i = 0; i < kLpcOrd; ++i) a_out[i] = a[i];
+    *err = e;
+}
+
+constexpr int kStatWarps = 4;
+
+__global__ void __launch_bounds__(kStatWarps * 32) rapt_stat_kernel(const RaptParams p)
+{
+    __shared__ float s_w479[kStatW], s_w480[kStatW];
+    __shared__ float s_d[kStatWarps][kStatW];
+    __shared__ float s_r[kStatWarps][2][kLpcOrd + 2];   // stabilised autocorrelation: [0]=cur [1]=prev
+    __shared__ float s_a[kStatWarps][kLpcOrd + 2];
+    __shared__ float s_b[kStatWarps][kLpcOrd + 2];
+    for (int t = threadIdx.x; t < kStatW; t += blockDim.x) {
+        s_w479[t] = (t < kStatW - 1) ? p.w479[t] : 0.0f;
+        s_w480[t] = p.w480[t];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long gf = blockIdx.x * static_cast<long long>(kStatWarps) + w;
+    if (gf >= p.total_fr) return;
+    const int u = find_segment(p.fr_offs, p.n, gf);
+    const RaptUtt ut = p.utts[u];
+    const int g = static_cast<int>(gf - ut.fr_off);
+    if (g < 2) {
+        if (lane == 0) {
+            p.sta[gf] = (g == 0) ? (0.01f * 0.2f) : static_cast<float>(0.2 / 10.0f);
+            p.rr[gf] = 1.0f;
+        }
+        return;
+    }
+    const float *x = p.wav + ut.wav_off;
+    float *d = s_d[w];
+    float rms[2] = {0.0f, 0.0f};
+    const int wsize = kStatW - 1;
+    for (int which = 0; which < 2; ++which) {
+        const float *win = x + static_cast<long long>(g) * kHop - (which == 0 ? 80 : 400);
+        for (int t = lane; t < wsize; t += 32)
+            d[t] = s_w479[t] * ((win[t + 1] * 32768.0f) - (c_rapt.preemp * (win[t] * 32768.0f)));
+        __syncwarp();
+        float acc = 0.0f;
+        if (lane == 0) {
+            for (int j = 0; j < wsize; ++j) acc += d[j] * d[j];
+        } else if (lane <= kLpcOrd) {
+            for (int j = 0; j < wsize - lane; ++j) acc += d[j] * d[j + lane];
+        } else if (lane == kLpcOrd + 1) {
+            for (int j = 0; j < kStatW; ++j) {
+                const float f = s_w480[j] * (win[j] * 32768.0f);
+                acc += f * f;
+            }
+            acc = static_cast<float>(sqrt(static_cast<double>(acc / kStatW)));
+        }
+        const float sum0 = __shfl_sync(0xffffffffu, acc, 0);
+        rms[which] = __shfl_sync(0xffffffffu, acc, kLpcOrd + 1);
+        float rv;
+        if (sum0 == 0.0f) {
+            rv = (lane == 0) ? 1.0f : 0.0f;
+        } else {
+            const float inv = 1.0 / sum0;
+            rv = (lane == 0) ? 1.0f : c_rapt.ffact * (acc * inv);
+        }
+        if (lane <= kLpcOrd) s_r[w][which][lane] = rv;
+        __syncwarp();
+    }
+    float a2[kLpcOrd], a1[kLpcOrd], err3, err1;
+    durbin18(s_r[w][0], a2, &err3);
+    durbin18(s_r[w][1], a1, &err1);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kLpcOrd; ++i) s_a[w][i] = a2[i];
+    }
+    __syncwarp();
+    // b = autocorrelation of the current inverse filter (a_to_aca)
+    const float *a = s_a[w];
+    if (lane < kLpcOrd) {
+        const int i = lane + 1;
+        float s = a[i - 1];
+        for (int j = 0; j < kLpcOrd - i; ++j) s += (a[j] * a[j + i]);
+        s_b[w][lane] = 2. * s;
+    } else if (lane == kLpcOrd) {
+        float s = 1.;
+        for (int i = 0; i < kLpcOrd; ++i) s += a[i] * a[i];
+        s_b[w][kLpcOrd] = s;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float s = s_b[w][kLpcOrd];
+        for (int i = 0; i < kLpcOrd; ++i) s += s_r[w][1][i + 1] * s_b[w][i];
+        const float t = (s / err1) - .8;
+        p.rr[gf] = (0.001 + rms[0]) / rms[1];
+        p.sta[gf] = static_cast<float>(0.2 / t);
+    }
+    (void)a1;
+    (void)err3;
+}
+
+// ---- K4 ------------------------------------------------------------------------------------
+constexpr int kDpWarps = 4;
+
+__global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams p)
+{
+    __shared__ unsigned char s_ring[kDpWarps][kRing][kCMax];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int u = blockIdx.x * kDpWarps + w;
+    if (u >= p.n) return;
+    const RaptUtt ut = p.utts[u];
+    const RaptCfg &cf = c_rapt.cfg[ut.cfg];
+    const float *ferr_tab = p.ferr + cf.table_off;
+    float *out = p.out + ut.out_off;
+    unsigned char(*ring)[kCMax] = s_ring[w];
+    const unsigned full_mask = 0xffffffffu;
+
+    float d_prev = 0.0f;
+    int loc_prev = -1, ncandp = 0;
+    int head = -1, tail = 0, num_active = 0;
+    int my_pre = 0;
+    for (int r = 0; r <= ut.R_last; ++r) {
+        const int nfr = (r < ut.R_last) ? cf.F : ut.nl;
+        const bool last_time = (r == ut.R_last);
+        num_active += nfr;
+        for (int i = 0; i < nfr; ++i) {
+            const int g = r * cf.F + i;
+            const long long gf = ut.fr_off + g;
+            const int ncand = p.ncand[gf];
+            const int loc = (lane < ncand) ? p.loc[gf * kCMax + lane] : -1;
+            const float mp = (lane < ncand) ? p.mp[gf * kCMax + lane] : 0.0f;
+            const float sta = p.sta[gf], rr = p.rr[gf];
+            const float v_from_uv = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a / rr);
+            const float uv_from_v = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr);
+            float errmin = FLT_MAX;
+            int minloc = 0;
+#pragma unroll
+            for (int j = 0; j < kCMax; ++j) {
+                const int loc1 = __shfl_sync(full_mask, loc_prev, j);
+                const float dp = __shfl_sync(full_mask, d_prev, j);
+                if (j < ncandp) {
+                    float ferr;
+                    if (loc > 0)
+                        ferr = (loc1 > 0) ? ferr_tab[(loc1 - cf.start) * cf.nlags + (loc - cf.start)] : v_from_uv;
+                    else
+                        ferr = (loc1 > 0) ? uv_from_v : 0.0f;
+                    const float err = ferr + dp;
+                    if (err < errmin) { errmin = err; minloc = j; }
+                }
+            }
+            float dcur;
+            if (g == 0) { dcur = mp; my_pre = 0; }
+            else { dcur = errmin + mp; my_pre = minloc; }
+            if (lane < kCMax) ring[g & (kRing - 1)][lane] = static_cast<unsigned char>(my_pre);
+            d_prev = dcur;
+            loc_prev = loc;
+            ncandp = ncand;
+            head = g;
+        }
+        __syncwarp();
+        // ---- commit: back-track from a frame where all surviving paths agree ------------------
+        if (head >= 0 && (num_active >= c_rapt.size_frame_hist || last_time)) {
+            const int num_paths = ncandp;
+            // best candidate of the newest frame: first minimum of the accumulated cost
+            float bv = (lane < num_paths) ? d_prev : FLT_MAX;
+            int bi = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(full_mask, bv, o);
+                const int oi = __shfl_xor_sync(full_mask, bi, o);
+                if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            int best_cand = bi;
+            int pc = (lane < num_paths) ? my_pre : 0;
+            int cmpth = -1;
+            bool done = true;
+            if (last_time) {
+                cmpth = head;
+            } else {
+                int frm = head;
+                while (true) {
+                    frm -= 1;
+                    const int v0 = __shfl_sync(full_mask, pc, 0);
+                    done = __all_sync(full_mask, (lane >= num_paths) || (pc == v0));
+                    if (!done) {
+                        if (lane < num_paths) pc = ring[frm & (kRing - 1)][pc];
+                    } else {
+                        cmpth = frm;
+                        best_cand = v0;
+                        break;
+                    }
+                    if (frm <= tail) {
+                        if (num_active < c_rapt.size_frame_out) { done = false; cmpth = -1; }
+                        else { done = true; cmpth = head; }
+                        break;
+                    }
+                }
+            }
+            if (done) {
+                if (lane == 0) {
+                    int bc = best_cand;
+                    for (int frm = cmpth; frm >= tail; --frm) {
+                        const float f0 = p.f0c[(ut.fr_off + frm) * kCMax + bc];
+                        out[frm] = (f0 == 0.0f) ? kUnvoiced : static_cast<float>(log(static_cast<double>(f0)));
+                        bc = ring[frm & (kRing - 1)][bc];
+                    }
+                }
+                num_active -= (cmpth - tail + 1);
+                tail = cmpth + 1;
+            }
+        }
+        __syncwarp();
+    }
+    for (int t = ut.n_fr + lane; t < ut.n_out; t += 32) out[t] = kUnvoiced;
+    if (head < 0)
+        for (int t = lane; t < ut.n_fr; t += 32) out[t] = kUnvoiced;
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static int iround(double x) { return static_cast<int>(x + 0.5); }
+
+int init_rapt(ssfe_ctx *ctx)
+{
+    RaptTables *T = new RaptTables();
+    ctx->rapt = T;
+    RaptConsts &h = T->host;
+    memset(&h, 0, sizeof(h));
+    const double freq = 16000.0;
+    // ESPS defaults installed by SPTK's rapt(); single precision like F0_params
+    const float cand_thresh = 0.3f, lag_weight = 0.3f, freq_weight = 0.02f, trans_cost = 0.005f, trans_amp = 0.5f,
+                trans_spec = 0.5f, voice_bias = 0.0f, double_cost = 0.35f, wind_dur = 0.0075f;
+    const float frame_step = static_cast<float>(256.0 / freq);
+    const int step = iround(frame_step * freq), size = iround(wind_dur * freq);
+    const float frame_int = static_cast<float>(static_cast<float>(step) / freq);
+    if (step != kHop || size != kWin) return set_error(ctx, SSFE_ERR_INVALID, "RAPT geometry mismatch");
+    h.cand_thresh = cand_thresh;
+    h.tcost = trans_cost;
+    h.tfact_a = trans_amp;
+    h.tfact_s = trans_spec;
+    h.vbias = voice_bias;
+    h.preemp = 0.4f;
+    h.ffact = static_cast<float>(1.0 / (1.0 + exp((-30.0f / 20.0) * log(10.0))));
+    h.size_frame_hist = static_cast<int>(0.5 / frame_int);
+    h.size_frame_out = static_cast<int>(1.0 / frame_int);
+    const float ln2 = static_cast<float>(log(2.0));
+    const float freqwt = freq_weight / frame_int;
+    const float ranges[2][2] = {{50.0f, 250.0f}, {100.0f, 600.0f}};
+    std::vector<float> ferr;
+    for (int c = 0; c < 2; ++c) {
+        RaptCfg &cf = h.cfg[c];
+        cf.start = iround(freq / ranges[c][1]);
+        cf.stop = iround(freq / ranges[c][0]);
+        cf.nlags = cf.stop - cf.start + 1;
+        cf.ncomp = size + cf.stop + 1;
+        const int i = static_cast<int>(0.2 * freq);
+        cf.F = (cf.ncomp >= step) ? ((i - cf.ncomp) / step) + 1 : i / step;
+        const int downpatch = ((static_cast<int>(freq * 0.005)) + 1) / 2;
+        const int stat_wsize = static_cast<int>(0.030 * freq), agap = static_cast<int>(0.020 * freq);
+        const int ind = (agap - stat_wsize) / 2, i2 = stat_wsize + ind;
+        cf.pad = downpatch + ((i2 > cf.ncomp) ? i2 : cf.ncomp);
+        cf.buff_size = cf.F * step + cf.pad;
+        cf.sdstep = cf.F * step;
+        cf.decnlags = 1 + (cf.nlags / kDec);
+        cf.decstart = std::max(1, cf.start / kDec);
+        cf.decsize = 1 + (size / kDec);
+        cf.n_el = cf.decsize + cf.decstart + cf.decnlags;
+        cf.lagwt = lag_weight / cf.stop;
+        cf.lag_wt = lag_weight / cf.nlags;
+        cf.table_off = static_cast<int>(ferr.size());
+        if (cf.ncomp > 448 || cf.nlags + 8 > kCcMax || cf.n_el > 64)
+            return set_error(ctx, SSFE_ERR_INVALID, "RAPT range does not fit the kernel buffers");
+        // voiced -> voiced frequency-jump cost, with the original's precision mix, on the host so
+        // that log() is the same libm the CPU path uses
+        for (int l1 = cf.start; l1 <= cf.stop; ++l1)
+            for (int l2 = cf.start; l2 <= cf.stop; ++l2) {
+                float ftemp = log((static_cast<double>(l2)) / l1);
+                float ttemp = fabs(ftemp);
+                float ft1 = double_cost + fabs(ftemp + ln2);
+                if (ttemp > ft1) ttemp = ft1;
+                ft1 = double_cost + fabs(ftemp - ln2);
+                if (ttemp > ft1) ttemp = ft1;
+                ferr.push_back(ttemp * freqwt);
+            }
+    }
+    // decimation filter: Hanning-windowed sinc, 81 taps, cut-off 0.5/8 cycles per sample
+    {
+        int nf = (static_cast<int>(freq * .005)) | 1;
+        const float fc = .5 / kDec;
+        if ((nf % 2) != 1) nf = nf + 1;
+        const int n = (nf + 1) / 2;
+        if (nf != kNco) return set_error(ctx, SSFE_ERR_INVALID, "RAPT decimator size mismatch");
+        std::vector<float> coef(n);
+        const double twopi = M_PI * 2.0;
+        coef[0] = 2.0 * fc;
+        const double c = M_PI;
+        double fn = twopi * fc;
+        for (int i = 1; i < n; ++i) coef[i] = sin(i * fn) / (c * i);
+        fn = twopi / static_cast<double>(nf);
+        for (int i = 0; i < n; ++i) coef[n - i - 1] *= (.5 - (.5 * cos(fn * (static_cast<double>(i) + 0.5))));
+        for (int i = 0; i < n - 1; ++i) h.co[i] = h.co[nf - 1 - i] = coef[n - 1 - i];
+        h.co[n - 1] = coef[0];
+    }
+    std::vector<float> w479(kStatW, 0.0f), w480(kStatW, 0.0f);
+    for (int n = kStatW - 1; n <= kStatW; ++n) {
+        std::vector<float> &wv = (n == kStatW) ? w480 : w479;
+        const double arg = 3.1415927 * 2.0 / n, half = 0.5;
+        for (int i = 0; i < n; ++i) wv[i] = (half - half * cos((half + static_cast<double>(i)) * arg));
+    }
+    SSFE_CUDA(ctx, cudaMalloc(&T->d_ferr, ferr.size() * sizeof(float)));
+    SSFE_CUDA(ctx, cudaMalloc(&T->d_w479, kStatW * sizeof(float)));
+    SSFE_CUDA(ctx, cudaMalloc(&T->d_w480, kStatW * sizeof(float)));
+    SSFE_CUDA(ctx, cudaMemcpy(T->d_ferr, ferr.data(), ferr.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSFE_CUDA(ctx, cudaMemcpy(T->d_w479, w479.data(), kStatW * sizeof(float), cudaMemcpyHostToDevice));
+    SSFE_CUDA(ctx, cudaMemcpy(T->d_w480, w480.data(), kStatW * sizeof(float), cudaMemcpyHostToDevice));
+    SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_rapt, &h, sizeof(h)));
+    return SSFE_OK;
+}
+
+void free_rapt(ssfe_ctx *ctx)
+{
+    if (!ctx->rapt) return;
+    cudaFree(ctx->rapt->d_ferr);
+    cudaFree(ctx->rapt->d_w479);
+    cudaFree(ctx->rapt->d_w480);
+    delete ctx->rapt;
+    ctx->rapt = nullptr;
+}
+
+int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, const int64_t *len_host,
+             const int64_t *frame_off_host, int n, const float *f0_lo, const float *f0_hi, float *f0_dev)
+{
+    if (n == 0) return SSFE_OK;
+    const RaptConsts &h = ctx->rapt->host;
+    std::vector<RaptUtt> utts(n);
+    std::vector<long long> fr_offs(n + 1), ds_offs(n + 1);
+    long long fr = 0, dsn = 0;
+    for (int i = 0; i < n; ++i) {
+        RaptUtt &ut = utts[i];
+        memset(&ut, 0, sizeof(ut));
+        const int64_t L = len_host[i];
+        if (L < 632)   // ((frame_step * 2) + wind_dur) * fs
+            return set_error(ctx, SSFE_ERR_TOO_SHORT, "utterance %d: input range too small for analysis by get_f0", i);
+        if (L > 0x7fffffff / 2) return set_error(ctx, SSFE_ERR_INVALID, "utterance %d too long for RAPT", i);
+        ut.cfg = (f0_lo[i] == 50.0f && f0_hi[i] == 250.0f) ? 0 : 1;
+        if (ut.cfg == 1 && !(f0_lo[i] == 100.0f && f0_hi[i] == 600.0f))
+            return set_error(ctx, SSFE_ERR_GENDER, "utterance %d: unsupported F0 range (%g, %g)", i, f0_lo[i], f0_hi[i]);
+        const RaptCfg &cf = h.cfg[ut.cfg];
+        ut.L = static_cast<int>(L);
+        ut.wav_off = start_host[i];
+        ut.out_off = frame_off_host[i];
+        ut.n_out = static_cast<int>(frame_off_host[i + 1] - frame_off_host[i]);
+        ut.R_last = (L > cf.buff_size) ? static_cast<int>((L - cf.buff_size + cf.sdstep - 1) / cf.sdstep) : 0;
+        const int64_t rem = L - static_cast<int64_t>(ut.R_last) * cf.sdstep;
+        ut.nl = (rem < cf.pad) ? 0 : static_cast<int>((rem - cf.pad) / kHop);
+        ut.n_fr = ut.R_last * cf.F + ut.nl;
+        if (ut.n_fr > ut.n_out) return set_error(ctx, SSFE_ERR_INVALID, "utterance %d: frame count mismatch", i);
+        ut.n_ds = static_cast<int>(L / kDec) + 8;
+        ut.fr_off = fr;
+        ut.ds_off = dsn;
+        fr_offs[i] = fr;
+        ds_offs[i] = dsn;
+        fr += ut.n_fr;
+        dsn += ut.n_ds;
+    }
+    fr_offs[n] = fr;
+    ds_offs[n] = dsn;
+
+    int rc;
+    if ((rc = ensure(ctx, ctx->ws.rapt_ds, dsn * sizeof(float)))) return rc;
+    const size_t per_fr = kCMax * (sizeof(short) + 2 * sizeof(float)) + 2 * sizeof(float) + 8;
+    if ((rc = ensure(ctx, ctx->ws.rapt_cand, (fr + 8) * per_fr))) return rc;
+
+    RaptParams p;
+    memset(&p, 0, sizeof(p));
+    p.wav = wav_base;
+    p.utts = upload(ctx, utts.data(), n);
+    p.fr_offs = upload(ctx, fr_offs.data(), n + 1);
+    p.ds_offs = upload(ctx, ds_offs.data(), n + 1);
+    if (!p.utts || !p.fr_offs || !p.ds_offs) return SSFE_ERR_NOMEM;
+    p.n = n;
+    p.total_fr = fr;
+    p.total_ds = dsn;
+    p.ds = static_cast<float *>(ctx->ws.rapt_ds.p);
+    char *base = static_cast<char *>(ctx->ws.rapt_cand.p);
+    const long long frp = fr + 8;
+    p.mp = reinterpret_cast<float *>(base);
+    p.f0c = p.mp + frp * kCMax;
+    p.sta = p.f0c + frp * kCMax;
+    p.rr = p.sta + frp;
+    p.loc = reinterpret_cast<short *>(p.rr + frp);
+    p.ncand = reinterpret_cast<unsigned char *>(p.loc + frp * kCMax);
+    p.ferr = ctx->rapt->d_ferr;
+    p.w479 = ctx->rapt->d_w479;
+    p.w480 = ctx->rapt->d_w480;
+    p.out = f0_dev;
+
+    RaptTables *T = ctx->rapt;
+    T->last_fr = fr;
+    T->last_ncand = p.ncand;
+    T->last_loc = p.loc;
+    T->last_mp = p.mp;
+    T->last_f0c = p.f0c;
+    T->last_sta = p.sta;
+    T->last_rr = p.rr;
+
+    cudaStream_t st = ctx->stream;
+    rapt_decimate_kernel<<<static_cast<unsigned>((dsn + 255) / 256), 256, 0, st>>>(p);
+    SSFE_LAUNCHED(ctx);
+    if (fr > 0) {
+        rapt_cand_kernel<<<static_cast<unsigned>((fr + kCandWarps - 1) / kCandWarps), kCandWarps * 32, 0, st>>>(p);
+        SSFE_LAUNCHED(ctx);
+        rapt_stat_kernel<<<static_cast<unsigned>((fr + kStatWarps - 1) / kStatWarps), kStatWarps * 32, 0, st>>>(p);
+        SSFE_LAUNCHED(ctx);
+    }
+    rapt_dp_kernel<<<static_cast<unsigned>((n + kDpWarps - 1) / kDpWarps), kDpWarps * 32, 0, st>>>(p);
+    SSFE_LAUNCHED(ctx);
+    return SSFE_OK;
+}
+
 }  // namespace ssfe
+
+// diagnostics: per-frame records of the most recent RAPT run (synchronous)
+extern "C" int64_t ssfe_rapt_dump(ssfe_ctx *ctx, int64_t max_frames, uint8_t *ncand, int16_t *loc, float *mp,
+                                  float *f0cand, float *stat, float *rms_ratio)
+{
+    if (!ctx || !ctx->rapt) return SSFE_ERR_INVALID;
+    const ssfe::RaptTables *T = ctx->rapt;
+    const long long n = std::min<long long>(T->last_fr, max_frames);
+    if (n <= 0) return 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return SSFE_ERR_CUDA;
+    cudaError_t e = cudaSuccess;
+    if (ncand && e == cudaSuccess) e = cudaMemcpy(ncand, T->last_ncand, n, cudaMemcpyDeviceToHost);
+    if (loc && e == cudaSuccess) e = cudaMemcpy(loc, T->last_loc, n * ssfe::kCMax * sizeof(short), cudaMemcpyDeviceToHost);
+    if (mp && e == cudaSuccess) e = cudaMemcpy(mp, T->last_mp, n * ssfe::kCMax * sizeof(float), cudaMemcpyDeviceToHost);
+    if (f0cand && e == cudaSuccess) e = cudaMemcpy(f0cand, T->last_f0c, n * ssfe::kCMax * sizeof(float), cudaMemcpyDeviceToHost);
+    if (stat && e == cudaSuccess) e = cudaMemcpy(stat, T->last_sta, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (rms_ratio && e == cudaSuccess) e = cudaMemcpy(rms_ratio, T->last_rr, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return ssfe::cuda_fail(ctx, e, "ssfe_rapt_dump");
+    return n;
+}

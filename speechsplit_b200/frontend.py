@@ -212,6 +212,17 @@ class FrontEnd:
                                            _ptr(lo, L.c_f32p), _ptr(hi, L.c_f32p), L.vp(out.data_ptr())))
         return out, np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
 
+    def rapt_dump(self, max_frames):
+        """Per-frame records of the most recent RAPT run (diagnostics for the parity tests)."""
+        m = int(max_frames)
+        d = dict(ncands=np.zeros(m, np.uint8), locs=np.zeros((m, 20), np.int16), mpvals=np.zeros((m, 20), np.float32),
+                 f0cand=np.zeros((m, 20), np.float32), stat=np.zeros(m, np.float32), rms_ratio=np.zeros(m, np.float32))
+        n = self.lib.ssfe_rapt_dump(self._h, m, *[L.vp(d[k].ctypes.data) for k in
+                                                  ("ncands", "locs", "mpvals", "f0cand", "stat", "rms_ratio")])
+        if n < 0:
+            self._check(int(n))
+        return {k: v[:n] for k, v in d.items()}
+
     def f0_normalize(self, f0, frame_offsets):
         """make_spect_f0.py:65-67 per utterance -> (f0_norm f32, stats f32 [n,2])."""
         f0 = self._dev(f0, torch.float32)

@@ -1,0 +1,165 @@
+"""GPU parity of the whole hot loop (ssfe_extract / ssfe_extract_host through the C ABI) against
+the reference-generated golden vectors and the oracle pipeline.
+
+Tolerances (BASELINE.json north_star): normalised mel <= 1e-4 abs; quantised-F0 bins and voicing
+flags identical on >= 99.9 % of frames; F0 within 1 cent on frames voiced in both; frame counts
+identical.  With the sequential filtfilt validation mode the RAPT input is bit-identical to the
+oracle's, and every F0 / bin must match exactly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from numpy.random import RandomState
+
+from oracle import ref_pipeline as rp
+from speechsplit_b200.corpus import make_manifest, pcm_to_float64, synth_batch
+
+pytestmark = pytest.mark.gpu
+UNV = np.float32(-1e10)
+
+
+def _golden_batch(golden_dir, names):
+    pcm, meta = [], []
+    for name in names:
+        g = np.load(os.path.join(golden_dir, name))
+        spk, gender = str(g["spk"]), str(g["gender"])
+        skip = 0
+        for k in range(int(g["n"])):
+            p = g["pcm%d" % k]
+            pcm.append(p)
+            meta.append(dict(spk=spk, gender=gender, skip=skip, S=g["S%d" % k], f0=g["f0_rapt%d" % k],
+                             f0n=g["f0_norm%d" % k], bins=g["bins%d" % k].astype(np.int64),
+                             wav=g["wav0"] if k == 0 else None))
+            L = p.shape[0]
+            skip += L + (1 if L % 256 == 0 else 0)
+    return pcm, meta
+
+
+def _extract(fe, pcm, meta, want, dtype=torch.int16):
+    off = np.concatenate([[0], np.cumsum([len(p) for p in pcm])]).astype(np.int64)
+    x = torch.from_numpy(np.concatenate(pcm))
+    if dtype != torch.int16:
+        x = (x.double() / 32768.0).to(dtype)
+    lo = [50.0 if m["gender"] == "M" else 100.0 for m in meta]
+    hi = [250.0 if m["gender"] == "M" else 600.0 for m in meta]
+    seed = [int(m["spk"][1:]) for m in meta]
+    skip = [m["skip"] for m in meta]
+    return fe.extract(x, off, lo, hi, seed, skip, want=want)
+
+
+def _check_against(res, meta, exact_f0):
+    fo, fx = res["frame_offsets"], res["fixed_offsets"]
+    mel = res["mel"].cpu().numpy()
+    f0n = res["f0_norm"].cpu().numpy()
+    f0 = res["f0_raw"].cpu().numpy()
+    bins = res["bins"].cpu().numpy()
+    onehot = res["onehot"].cpu().numpy()
+    n_fr = n_same = 0
+    worst_mel = worst_cent = 0.0
+    for i, m in enumerate(meta):
+        S = mel[fo[i]:fo[i + 1]]
+        assert S.shape == m["S"].shape and S.dtype == np.float32            # len(S) == len(f0_rapt), :69
+        worst_mel = max(worst_mel, float(np.abs(S - m["S"]).max()))
+        g_f0, g_bins, g_f0n = f0[fo[i]:fo[i + 1]], bins[fo[i]:fo[i + 1]], f0n[fo[i]:fo[i + 1]]
+        assert g_f0.shape == m["f0"].shape
+        same = (g_bins == m["bins"]) & ((g_f0 == UNV) == (m["f0"] == UNV))
+        n_fr += same.size
+        n_same += int(same.sum())
+        both = (g_f0 != UNV) & (m["f0"] != UNV)
+        if both.any():
+            worst_cent = max(worst_cent, float(1731.234 * np.abs(g_f0[both] - m["f0"][both]).max()))
+        if exact_f0:
+            assert np.array_equal(g_f0, m["f0"]) and np.array_equal(g_f0n, m["f0n"], equal_nan=True)
+            assert np.array_equal(g_bins, m["bins"])
+        # one-hot consistent with bins: exactly quantize_f0_numpy's encoding
+        enc = onehot[fo[i]:fo[i + 1]]
+        assert enc.shape == (len(g_bins), 257) and np.array_equal(enc.argmax(1), g_bins) and np.all(enc.sum(1) == 1)
+        if m["wav"] is not None:
+            w = res["wav64"].cpu().numpy()[fx[i]:fx[i + 1]]
+            assert np.abs(w - m["wav"]).max() <= (1e-12 if exact_f0 else 1e-6)
+    assert worst_mel <= 1e-4, worst_mel
+    assert n_same >= 0.999 * n_fr, (n_same, n_fr)
+    assert worst_cent <= 1.0, worst_cent
+    return worst_mel, n_same / n_fr, worst_cent
+
+
+WANT = ("mel", "f0_norm", "f0_raw", "bins", "onehot", "wav", "wav64")
+NAMES = ["pipeline_p226.npz", "pipeline_p225.npz"]
+
+
+def test_extract_golden_scan_mode(fe, golden_dir):
+    pcm, meta = _golden_batch(golden_dir, NAMES)
+    res = _extract(fe, pcm, meta, WANT)
+    _check_against(res, meta, exact_f0=False)
+
+
+def test_extract_golden_sequential_mode_is_exact(fe_seq, golden_dir):
+    pcm, meta = _golden_batch(golden_dir, NAMES)
+    res = _extract(fe_seq, pcm, meta, WANT)
+    _check_against(res, meta, exact_f0=True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_extract_input_dtypes(fe, golden_dir, dtype):
+    pcm, meta = _golden_batch(golden_dir, NAMES[:1])
+    a = _extract(fe, pcm, meta, ("mel", "f0_norm", "bins"))
+    b = _extract(fe, pcm, meta, ("mel", "f0_norm", "bins"), dtype=dtype)
+    for k in ("mel", "f0_norm", "bins"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_extract_batch_order_and_split_invariance(fe, golden_dir):
+    """Utterances are independent given (seed, skip): shuffling the batch or running each utterance
+    alone gives bit-identical results - the property the multi-GPU sharding relies on."""
+    pcm, meta = _golden_batch(golden_dir, NAMES)
+    full = _extract(fe, pcm, meta, ("mel", "f0_norm", "bins"))
+    fo = full["frame_offsets"]
+    perm = [3, 0, 4, 2, 1]
+    sh = _extract(fe, [pcm[i] for i in perm], [meta[i] for i in perm], ("mel", "f0_norm", "bins"))
+    so = sh["frame_offsets"]
+    for k, i in enumerate(perm):
+        for name in ("mel", "f0_norm", "bins"):
+            assert torch.equal(sh[name][so[k]:so[k + 1]], full[name][fo[i]:fo[i + 1]]), (name, i)
+    for i in range(len(pcm)):
+        one = _extract(fe, [pcm[i]], [meta[i]], ("mel", "f0_norm", "bins"))
+        for name in ("mel", "f0_norm", "bins"):
+            assert torch.equal(one[name], full[name][fo[i]:fo[i + 1]]), (name, i)
+
+
+def test_extract_host_matches_device_path(fe, golden_dir):
+    pcm, meta = _golden_batch(golden_dir, NAMES)
+    res = _extract(fe, pcm, meta, ("mel", "f0_norm", "bins"))
+    off = np.concatenate([[0], np.cumsum([len(p) for p in pcm])]).astype(np.int64)
+    lo = [50.0 if m["gender"] == "M" else 100.0 for m in meta]
+    hi = [250.0 if m["gender"] == "M" else 600.0 for m in meta]
+    h = fe.extract_host(np.concatenate(pcm), off, lo, hi, [int(m["spk"][1:]) for m in meta],
+                        [m["skip"] for m in meta])
+    assert np.array_equal(h["mel"], res["mel"].cpu().numpy())
+    assert np.array_equal(h["f0_norm"], res["f0_norm"].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(h["bins"], res["bins"].cpu().numpy())
+
+
+def test_extract_vs_oracle_small_corpus(fe):
+    """A fresh synthetic mini-corpus (6 speakers x 4 files) against the oracle pipeline."""
+    metas = make_manifest(6, 4, seed=17)
+    pcm = [p.numpy() for p in synth_batch(metas)]
+    meta, cur, prng, skip = [], None, None, 0
+    for m, p in zip(metas, pcm):
+        if cur != m.spk:
+            cur, prng, skip = m.spk, RandomState(m.spk_id), 0
+        S, f0n, st = rp.extract_utterance(pcm_to_float64(p), m.gender, prng, want_stages=True)
+        meta.append(dict(spk=m.spk, gender=m.gender, skip=skip, S=S, f0=st["f0_rapt"], f0n=f0n,
+                         bins=rp.quantize_f0_numpy(f0n)[1], wav=None))
+        skip += len(p) + (1 if len(p) % 256 == 0 else 0)
+    res = _extract(fe, pcm, meta, WANT)
+    worst_mel, frac, cents = _check_against(res, meta, exact_f0=False)
+    print("mini-corpus: mel %.2e, identical frames %.5f, worst %.3f cent" % (worst_mel, frac, cents))
+
+
+def test_extract_errors(fe):
+    x = torch.zeros(500, dtype=torch.int16)
+    with pytest.raises(ValueError):
+        fe.extract(x, [0, 500], [50.0], [250.0], [226], [0])             # too short for get_f0
+    with pytest.raises(ValueError):
+        fe.extract(torch.zeros(5000, dtype=torch.int16), [0, 5000], [70.0], [250.0], [226], [0])   # not M / F
