@@ -36,7 +36,7 @@ typedef enum {
     SSFE_ERR_INVALID = -1,    /* bad argument / unsupported configuration                      */
     SSFE_ERR_CUDA = -2,       /* a CUDA runtime call failed (message has the CUDA error)       */
     SSFE_ERR_TOO_SHORT = -3,  /* utterance too short: filtfilt needs L > 18
-                                 (scipy ValueError), RAPT needs L >= 632 (pysptk ValueError)   */
+                                 (scipy ValueError), RAPT needs L >= 633 (pysptk ValueError)   */
     SSFE_ERR_RANGE = -4,      /* quantize_f0: value outside [0,1] -> reference AssertionError
                                  (utils.py:52 / :68)                                           */
     SSFE_ERR_NOMEM = -5,

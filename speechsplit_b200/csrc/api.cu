@@ -287,7 +287,7 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     int64_t pos = 0;
     for (int i = 0; i < n; ++i) {
         const int64_t Lf = fix[i + 1] - fix[i];
-        if (Lf < 632)   // ((2 * frame_step) + wind_dur) * fs, the get_f0 minimum
+        if (Lf < 633)   // get_f0 minimum ((2 * frame_step) + wind_dur) * fs = 632.00002 with float parameters
             return set_error(ctx, SSFE_ERR_TOO_SHORT, "utterance %d: input range too small for analysis by get_f0", i);
         seg[i] = pos;
         pos += (Lf + 2 * kHalfPad + kSegAlign - 1) / kSegAlign * kSegAlign;

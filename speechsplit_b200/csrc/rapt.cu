@@ -736,7 +736,9 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         RaptUtt &ut = utts[i];
         memset(&ut, 0, sizeof(ut));
         const int64_t L = len_host[i];
-        if (L < 632)   // ((frame_step * 2) + wind_dur) * fs
+        // get_f0's minimum: total_samps < ((frame_step * 2.0) + wind_dur) * fs with float parameters
+        // (0.016f and 0.0075f round up, so 632 samples are rejected and 633 accepted)
+        if (static_cast<double>(L) < ((static_cast<float>(256.0 / 16000.0) * 2.0) + 0.0075f) * 16000.0)
             return set_error(ctx, SSFE_ERR_TOO_SHORT, "utterance %d: input range too small for analysis by get_f0", i);
         if (L > 0x7fffffff / 2) return set_error(ctx, SSFE_ERR_INVALID, "utterance %d too long for RAPT", i);
         ut.cfg = (f0_lo[i] == 50.0f && f0_hi[i] == 250.0f) ? 0 : 1;

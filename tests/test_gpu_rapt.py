@@ -76,7 +76,7 @@ def test_rapt_bit_exact_small_corpus(fe):
     assert voiced > 500
 
 
-@pytest.mark.parametrize("L", [632, 700, 737, 1000, 3297, 3298, 3512, 6113, 6114, 48000 + 1, 16000])
+@pytest.mark.parametrize("L", [633, 700, 737, 1000, 3297, 3298, 3512, 6113, 6114, 48000 + 1, 16000])
 def test_rapt_lengths_and_read_boundaries(fe, L):
     """Lengths around the streaming read size (male 3297 / female 3512 samples) and the minimum."""
     rng = np.random.default_rng(L)
@@ -113,7 +113,9 @@ def test_rapt_long_form(fe):
 
 def test_rapt_too_short_and_bad_range(fe):
     with pytest.raises(ValueError):
-        fe.rapt(torch.zeros(600), [0, 600], [50.0], [250.0])
+        fe.rapt(torch.zeros(632), [0, 632], [50.0], [250.0])      # 632 < 632.00002 (float parameters)
+    with pytest.raises(ValueError):
+        rapt_ref(np.zeros(632, np.float32), 16000, 256, 50, 250)
     with pytest.raises(ValueError):
         fe.rapt(torch.zeros(6000), [0, 6000], [60.0], [240.0])
 
