@@ -78,6 +78,13 @@ const char *ssfe_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t ssfe_launch_count(const ssfe_ctx *ctx);
 
+/* In-stream CUDA-event timing of the stages of ssfe_extract (off by default).  ssfe_stage_ms waits
+ * for the most recent timed ssfe_extract and writes the milliseconds of, in order: rand (MT19937),
+ * filtfilt (+ dither combine), reflect edges, fused STFT-mel kernel, RAPT decimate, RAPT
+ * candidates, RAPT stationarity, RAPT Viterbi, F0 normalise/quantise.  Returns the stage count. */
+int  ssfe_enable_timing(ssfe_ctx *ctx, int on);
+int  ssfe_stage_ms(ssfe_ctx *ctx, float *ms_out, int n);
+
 /* ---- geometry (pure host helpers) --------------------------------------------------------- */
 /* make_spect_f0.py:52-53: a length that is a multiple of 256 grows by one sample (value 1e-06) */
 int64_t ssfe_fixed_length(int64_t n_samples);

@@ -51,6 +51,8 @@ SIGNATURES = {
     "ssfe_synchronize": (ctypes.c_int, [vp]),
     "ssfe_version": (ctypes.c_char_p, []),
     "ssfe_launch_count": (ctypes.c_int64, [vp]),
+    "ssfe_enable_timing": (ctypes.c_int, [vp, ctypes.c_int]),
+    "ssfe_stage_ms": (ctypes.c_int, [vp, c_f32p, ctypes.c_int]),
     "ssfe_fixed_length": (ctypes.c_int64, [ctypes.c_int64]),
     "ssfe_num_frames": (ctypes.c_int64, [ctypes.c_int64]),
     "ssfe_plan_offsets": (ctypes.c_int, [c_i64p, ctypes.c_int, c_i64p, c_i64p]),

@@ -96,9 +96,15 @@ def _control_tracks(meta: UttMeta, n_ctl: int):
     return f0, vg, ng, formants, peak, tilt
 
 
+def control_tracks(meta: UttMeta):
+    """Picklable per-utterance job (bench.py maps it over a process pool before CUDA starts)."""
+    return _control_tracks(meta, meta.length // 160 + 2)
+
+
 @torch.no_grad()
-def synth_batch(metas: Sequence[UttMeta], device="cpu", n_harm=14) -> List[torch.Tensor]:
-    """Synthesise utterances; returns one int16 tensor (length,) per meta, on ``device``."""
+def synth_batch(metas: Sequence[UttMeta], device="cpu", n_harm=14, tracks=None) -> List[torch.Tensor]:
+    """Synthesise utterances; returns one int16 tensor (length,) per meta, on ``device``.
+    ``tracks``: optional precomputed ``control_tracks(meta)`` results, same order."""
     if len(metas) == 0:
         return []
     dev = torch.device(device)
@@ -112,7 +118,10 @@ def synth_batch(metas: Sequence[UttMeta], device="cpu", n_harm=14) -> List[torch
     pk = np.zeros(B, np.float32)
     tl = np.zeros(B, np.float32)
     for i, m in enumerate(metas):
-        f0c[i], vgc[i], ngc[i], fm[i], pk[i], tl[i] = _control_tracks(m, n_ctl)
+        a, b_, c, fm[i], pk[i], tl[i] = tracks[i] if tracks is not None else control_tracks(m)
+        k = a.shape[0]
+        f0c[i, :k], vgc[i, :k], ngc[i, :k] = a, b_, c
+        f0c[i, k:] = a[-1]
 
     def up(a):
         ta = torch.from_numpy(a).to(dev)[:, None, :]

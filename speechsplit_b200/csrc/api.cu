@@ -77,9 +77,35 @@ void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
     return d;
 }
 
+void mark(ssfe_ctx *ctx, int boundary)
+{
+    if (!ctx->timing || boundary < 0 || boundary > ST_COUNT) return;
+    if (!ctx->ev[boundary]) cudaEventCreate(&ctx->ev[boundary]);
+    cudaEventRecord(ctx->ev[boundary], ctx->stream);
+    if (boundary + 1 > ctx->n_ev) ctx->n_ev = boundary + 1;
+}
+
 }  // namespace ssfe
 
 using namespace ssfe;
+
+extern "C" int ssfe_enable_timing(ssfe_ctx *ctx, int on)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    ctx->timing = on != 0;
+    ctx->n_ev = 0;
+    return SSFE_OK;
+}
+
+extern "C" int ssfe_stage_ms(ssfe_ctx *ctx, float *ms_out, int n)
+{
+    if (!ctx || !ms_out) return SSFE_ERR_INVALID;
+    if (ctx->n_ev < ST_COUNT + 1) return set_error(ctx, SSFE_ERR_INVALID, "no timed ssfe_extract call yet");
+    SSFE_CUDA(ctx, cudaEventSynchronize(ctx->ev[ST_COUNT]));
+    for (int i = 0; i < n && i < ST_COUNT; ++i)
+        SSFE_CUDA(ctx, cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
+    return ST_COUNT;
+}
 
 extern "C" const char *ssfe_version(void) { return "ssfe 0.1 (sm_100a)"; }
 
@@ -181,6 +207,8 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     if (ctx->meta_dev) cudaFree(ctx->meta_dev);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    for (cudaEvent_t e : ctx->ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -303,7 +331,9 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     float *wavp = static_cast<float *>(ctx->ws.wavp.p);
     double *dith = static_cast<double *>(ctx->ws.dith.p);
 
+    mark(ctx, ST_RAND);
     if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith))) return rc;
+    mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
     if (!d_seg || !d_fix) return SSFE_ERR_NOMEM;
@@ -314,8 +344,11 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     fo.wav = o->wav;
     fo.wav64 = o->wav64;
     if ((rc = filtfilt_run(ctx, x_dev, dtype, b->sample_offsets, fix.data(), n, fo))) return rc;
+    mark(ctx, ST_EDGES);
     if ((rc = fill_reflect_edges(ctx, wavp, d_seg, d_fix, n))) return rc;
+    mark(ctx, ST_STFT);
     if ((rc = stft_padded(ctx, wavp, seg.data(), frames.data(), n, 0, o->mel))) return rc;
+    mark(ctx, ST_RAPT_DEC);
 
     float *f0_raw = o->f0_raw;
     if (!f0_raw) {
@@ -323,7 +356,10 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
         f0_raw = static_cast<float *>(ctx->ws.rapt_f0.p);
     }
     if ((rc = rapt_run(ctx, wavp, start.data(), len.data(), foff.data(), n, b->f0_lo, b->f0_hi, f0_raw))) return rc;
-    return f0_post_run(ctx, f0_raw, foff.data(), n, o->f0_norm, nullptr, o->onehot, o->bins);
+    mark(ctx, ST_POST);
+    rc = f0_post_run(ctx, f0_raw, foff.data(), n, o->f0_norm, nullptr, o->onehot, o->bins);
+    mark(ctx, ST_COUNT);
+    return rc;
 }
 }  // namespace ssfe
 

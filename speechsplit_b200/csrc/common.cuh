@@ -63,6 +63,10 @@ struct ssfe_ctx {
     ssfe::RaptTables *rapt = nullptr;
     ssfe::Workspace ws;
     // host staging for ssfe_extract_host
+    // optional in-stream stage timing of ssfe_extract (ssfe_enable_timing / ssfe_stage_ms)
+    bool timing = false;
+    cudaEvent_t ev[16] = {};
+    int n_ev = 0;
     void *pin_in = nullptr;  size_t pin_in_cap = 0;
     void *pin_out = nullptr; size_t pin_out_cap = 0;
     ssfe::DevBuf h_x, h_mel, h_f0, h_bins;
@@ -71,6 +75,10 @@ struct ssfe_ctx {
 namespace ssfe {
 
 int set_error(ssfe_ctx *ctx, int code, const char *fmt, ...);
+// stage boundaries of ssfe_extract, in launch order
+enum Stage { ST_RAND = 0, ST_FILTFILT, ST_EDGES, ST_STFT, ST_RAPT_DEC, ST_RAPT_CAND, ST_RAPT_STAT, ST_RAPT_DP,
+             ST_POST, ST_COUNT };
+void mark(ssfe_ctx *ctx, int boundary);     // records event `boundary` (0..ST_COUNT) when timing is on
 int cuda_fail(ssfe_ctx *ctx, cudaError_t e, const char *what);
 int ensure(ssfe_ctx *ctx, DevBuf &b, size_t bytes);
 // copies `bytes` of host metadata to the device through the pinned arena; returns device pointer

@@ -806,12 +806,17 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     cudaStream_t st = ctx->stream;
     rapt_decimate_kernel<<<static_cast<unsigned>((dsn + 255) / 256), 256, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
+    mark(ctx, ST_RAPT_CAND);
     if (fr > 0) {
         rapt_cand_kernel<<<static_cast<unsigned>((fr + kCandWarps - 1) / kCandWarps), kCandWarps * 32, 0, st>>>(p);
         SSFE_LAUNCHED(ctx);
+        mark(ctx, ST_RAPT_STAT);
         rapt_stat_kernel<<<static_cast<unsigned>((fr + kStatWarps - 1) / kStatWarps), kStatWarps * 32, 0, st>>>(p);
         SSFE_LAUNCHED(ctx);
+    } else {
+        mark(ctx, ST_RAPT_STAT);
     }
+    mark(ctx, ST_RAPT_DP);
     rapt_dp_kernel<<<static_cast<unsigned>((n + kDpWarps - 1) / kDpWarps), kDpWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     return SSFE_OK;

@@ -136,6 +136,19 @@ class FrontEnd:
     def launch_count(self):
         return int(self.lib.ssfe_launch_count(self._h))
 
+    STAGES = ("rand", "filtfilt", "edges", "stft_mel", "rapt_decimate", "rapt_cand", "rapt_stat", "rapt_dp", "f0_post")
+
+    def enable_timing(self, on=True):
+        self._check(self.lib.ssfe_enable_timing(self._h, 1 if on else 0))
+
+    def stage_ms(self):
+        """Milliseconds per stage of the most recent timed extract() (CUDA events on the launch stream)."""
+        buf = (ctypes.c_float * 16)()
+        n = self.lib.ssfe_stage_ms(self._h, buf, 16)
+        if n < 0:
+            self._check(n)
+        return {k: float(buf[i]) for i, k in enumerate(self.STAGES[:n])}
+
     def synchronize(self):
         self._check(self.lib.ssfe_synchronize(self._h))
 
