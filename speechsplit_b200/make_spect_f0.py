@@ -1,0 +1,113 @@
+"""Function / CLI form of the reference script ``make_spect_f0.py`` on the GPU.
+
+    python -m speechsplit_b200.make_spect_f0 [--root assets/wavs] [--out assets/spmel]
+                                             [--out-f0 assets/raptf0] [--spk2gen assets/spk2gen.pkl]
+
+Same inputs and outputs as the reference (make_spect_f0.py:19-25,71-74): ``<root>/<spk>/*.wav``
+at 16 kHz mono, a pickled dict speaker -> 'M' / 'F', speaker directories named ``p<int>``;
+writes ``<out>/<spk>/<utt>.npy`` (T, 80) float32 and ``<out-f0>/<spk>/<utt>.npy`` (T,) float32
+with ``np.save(..., allow_pickle=False)``.  The per-utterance loop body (:50-67) runs as one
+``ssfe_extract`` call per group of speakers; file I/O stays on the host (stdlib ``wave``; the
+reference's ``soundfile`` is used when importable).
+"""
+import argparse
+import os
+import pickle
+import wave
+
+import numpy as np
+
+from .frontend import GENDER_RANGE, default_frontend
+from .sharding import fixed_length
+
+
+def read_wav(path):
+    """-> (int16 or float array, fs).  16-bit PCM stays int16 (x = v/32768 exactly, like sf.read)."""
+    try:
+        import soundfile as sf
+        x, fs = sf.read(path, dtype="int16")
+        return x, fs
+    except ImportError:
+        with wave.open(path, "rb") as w:
+            fs, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n)
+        if sw != 2 or nch != 1:
+            raise ValueError("%s: only 16-bit mono PCM is supported without soundfile" % path)
+        return np.frombuffer(raw, dtype="<i2"), fs
+
+
+def extract_speakers(fe, speakers, max_utts_per_call=4096):
+    """speakers: list of (spk_name, gender, [arrays in sorted file order]).  Yields
+    (spk_name, file_index, S (T,80) f32, f0_norm (T,) f32) in the reference's loop order."""
+    batch, meta = [], []
+
+    def flush():
+        if not batch:
+            return
+        dt = np.int16 if all(a.dtype == np.int16 for a in batch) else np.float64
+        x = np.concatenate([a.astype(dt) if dt == np.int16 else (a.astype(np.float64) / 32768.0 if a.dtype == np.int16 else a.astype(np.float64)) for a in batch])
+        off = np.concatenate([[0], np.cumsum([len(a) for a in batch])]).astype(np.int64)
+        lo = [GENDER_RANGE[m[1]][0] for m in meta]
+        hi = [GENDER_RANGE[m[1]][1] for m in meta]
+        res = fe.extract_host(x, off, lo, hi, [m[2] for m in meta], [m[3] for m in meta], want_bins=False)
+        fo = res["frame_offsets"]
+        for i, m in enumerate(meta):
+            yield m[0], m[4], res["mel"][fo[i]:fo[i + 1]], res["f0_norm"][fo[i]:fo[i + 1]]
+        batch.clear()
+        meta.clear()
+
+    for spk, gender, utts in speakers:
+        if gender not in GENDER_RANGE:
+            raise ValueError                                   # make_spect_f0.py:45
+        seed = int(spk[1:])                                    # :47
+        skip = 0
+        for k, a in enumerate(utts):
+            batch.append(np.asarray(a))
+            meta.append((spk, gender, seed, skip, k))
+            skip += fixed_length(len(a))                       # the stream advances by the post-append length (:53,55)
+            if len(batch) >= max_utts_per_call:
+                yield from flush()
+    yield from flush()
+
+
+def make_spect_f0(root_dir="assets/wavs", target_dir="assets/spmel", target_dir_f0="assets/raptf0",
+                  spk2gen_path="assets/spk2gen.pkl", device=None, verbose=True):
+    spk2gen = pickle.load(open(spk2gen_path, "rb"))            # :19
+    fe = default_frontend(device)
+    dir_name, subdirs, _ = next(os.walk(root_dir))             # :28
+    if verbose:
+        print("Found directory: %s" % dir_name)
+    speakers, names = [], {}
+    for subdir in sorted(subdirs):                             # :31
+        if verbose:
+            print(subdir)
+        os.makedirs(os.path.join(target_dir, subdir), exist_ok=True)
+        os.makedirs(os.path.join(target_dir_f0, subdir), exist_ok=True)
+        _, _, files = next(os.walk(os.path.join(dir_name, subdir)))
+        files = sorted(files)                                  # :48
+        utts = []
+        for f in files:
+            x, fs = read_wav(os.path.join(dir_name, subdir, f))
+            assert fs == 16000                                 # :51
+            utts.append(x)
+        speakers.append((subdir, spk2gen[subdir], utts))
+        names[subdir] = files
+    for spk, k, S, f0n in extract_speakers(fe, speakers):
+        stem = names[spk][k][:-4]
+        np.save(os.path.join(target_dir, spk, stem), S.astype(np.float32), allow_pickle=False)        # :71-72
+        np.save(os.path.join(target_dir_f0, spk, stem), f0n.astype(np.float32), allow_pickle=False)   # :73-74
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("--root", default="assets/wavs")
+    ap.add_argument("--out", default="assets/spmel")
+    ap.add_argument("--out-f0", default="assets/raptf0")
+    ap.add_argument("--spk2gen", default="assets/spk2gen.pkl")
+    ap.add_argument("--device", type=int, default=None)
+    a = ap.parse_args()
+    make_spect_f0(a.root, a.out, a.out_f0, a.spk2gen, a.device)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+"""Host logic of the multi-GPU path, on CPU: LPT sharding, dither stream offsets, and a
+world-size-2 gloo run of the same barrier / max-over-ranks pattern bench.py uses."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from numpy.random import RandomState
+
+from speechsplit_b200.corpus import make_manifest
+from speechsplit_b200.sharding import dither_skips, fixed_length, lpt_shards
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fixed_length():
+    assert [fixed_length(n) for n in (255, 256, 257, 48000, 48128)] == [255, 257, 257, 48000, 48129]
+
+
+def test_dither_skips_follow_the_speaker_stream():
+    metas = make_manifest(3, 5, seed=4)
+    skips = dither_skips([m.spk for m in metas], [m.length for m in metas])
+    for spk in sorted({m.spk for m in metas}):
+        idx = [i for i, m in enumerate(metas) if m.spk == spk]
+        assert skips[idx[0]] == 0
+        prng = RandomState(int(spk[1:]))
+        pos = 0
+        for i in idx:                       # what make_spect_f0.py:47-55 does, file by file
+            assert skips[i] == pos
+            n = fixed_length(metas[i].length)
+            first = prng.rand(n)[0]
+            again = RandomState(int(spk[1:]))
+            again.rand(int(skips[i])) if skips[i] else None
+            assert again.rand(1)[0] == first
+            pos += n
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_lpt_shards_partition_and_balance(world):
+    metas = make_manifest(20, 30, seed=1)
+    lengths = np.array([m.length for m in metas])
+    shards = lpt_shards(lengths, world)
+    allidx = np.concatenate(shards)
+    assert sorted(allidx.tolist()) == list(range(len(metas)))           # a partition
+    loads = np.array([lengths[s].sum() for s in shards])
+    assert loads.max() - loads.min() <= lengths.max()                   # LPT bound
+    for s in shards:
+        assert np.all(np.diff(s) > 0)                                   # corpus order kept inside a shard
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from speechsplit_b200.corpus import make_manifest
+from speechsplit_b200.sharding import dither_skips, lpt_shards
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+metas = make_manifest(6, 10, seed=2)
+lengths = [m.length for m in metas]
+shard = lpt_shards(lengths, world)[rank]
+skips = dither_skips([m.spk for m in metas], lengths)[shard]
+mine = torch.tensor([float(sum(lengths[i] for i in shard))], dtype=torch.float64)
+tot = mine.clone(); dist.all_reduce(tot)
+assert abs(tot.item() - sum(lengths)) < 1e-6                 # every utterance is on exactly one rank
+t = torch.tensor([1.0 + rank], dtype=torch.float64)
+dist.barrier(); dist.all_reduce(t, op=dist.ReduceOp.MAX)     # bench.py: max over ranks
+assert t.item() == float(world)
+cnt = torch.tensor([len(shard)]); dist.all_reduce(cnt); assert cnt.item() == len(metas)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok", len(shard), int(skips.sum()))
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
