@@ -104,6 +104,9 @@ extern "C" int ssfe_stage_ms(ssfe_ctx *ctx, float *ms_out, int n)
     SSFE_CUDA(ctx, cudaEventSynchronize(ctx->ev[ST_COUNT]));
     for (int i = 0; i < n && i < ST_COUNT; ++i)
         SSFE_CUDA(ctx, cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
+    // the dither kernel runs on the side stream, overlapped with filtfilt: report its own duration
+    if (n > ST_RAND && cudaEventQuery(ctx->ev_aux1) == cudaSuccess)
+        cudaEventElapsedTime(&ms_out[ST_RAND], ctx->ev_aux0, ctx->ev_aux1);
     return ST_COUNT;
 }
 
@@ -170,6 +173,11 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
         if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
+        if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreate(&ctx->ev_aux0)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreate(&ctx->ev_aux1)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         ctx->stream = ctx->own_stream;
         if ((rc = init_stft_tables(ctx))) break;
         if ((rc = init_filtfilt(ctx))) break;
@@ -208,6 +216,9 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     for (cudaEvent_t e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_aux0, ctx->ev_aux1})
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -331,8 +342,10 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     float *wavp = static_cast<float *>(ctx->ws.wavp.p);
     double *dith = static_cast<double *>(ctx->ws.dith.p);
 
+    // the dither stream is independent of the signal until the very last filtfilt kernel: generate
+    // it on a side stream while the forward / backward-local passes run
     mark(ctx, ST_RAND);
-    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith))) return rc;
+    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
     mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
@@ -343,6 +356,7 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     fo.seg_off_dev = d_seg;
     fo.wav = o->wav;
     fo.wav64 = o->wav64;
+    fo.dith_ready = ctx->ev_join;
     if ((rc = filtfilt_run(ctx, x_dev, dtype, b->sample_offsets, fix.data(), n, fo))) return rc;
     mark(ctx, ST_EDGES);
     if ((rc = fill_reflect_edges(ctx, wavp, d_seg, d_fix, n))) return rc;

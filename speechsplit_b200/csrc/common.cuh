@@ -47,6 +47,8 @@ struct ssfe_ctx {
     int num_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // ssfe_extract_host pipeline
+    cudaStream_t aux = nullptr;                               // the dither stream runs beside filtfilt
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux0 = nullptr, ev_aux1 = nullptr;
     ssfe_config cfg;
     std::vector<float> mel_basis;      // host copy (513 x 80)
     char err[512];
@@ -135,14 +137,16 @@ struct FiltOut {
     const int64_t *seg_off_dev = nullptr;
     float *wav = nullptr;            // flat f32 [fixed offsets]
     double *wav64 = nullptr;
+    cudaEvent_t dith_ready = nullptr; // waited on right before the kernel that reads `dith`
 };
 int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_off_host,
                  const int64_t *fix_off_host, int n, const FiltOut &out);
 int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
                        const int64_t *fix_off_dev, int n);
 
+// launch_on: stream for the kernel (metadata still travels on ctx->stream; ordering handled inside)
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
-             int n, double *u_dev);
+             int n, double *u_dev, cudaStream_t launch_on = nullptr);
 
 int init_rapt(ssfe_ctx *ctx);
 void free_rapt(ssfe_ctx *ctx);

@@ -257,7 +257,7 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 }
 
 template <int DTYPE>
-static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential)
+static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gu = (p.n + 63) / 64;
@@ -277,6 +277,7 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential)
     }
     filt_carry_kernel<DTYPE, 1><<<gu, 64, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
+    if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
     filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     return SSFE_OK;
@@ -327,9 +328,9 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.wav64 = out.wav64;
     p.y1_out = static_cast<double *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }

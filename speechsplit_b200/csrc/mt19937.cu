@@ -5,10 +5,11 @@
 // ((a >> 5) * 2^26 + (b >> 6)) / 2^53 from two successive tempered 32-bit outputs.  A speaker's
 // stream continues across its files in sorted order, so utterance k starts `skip` doubles in.
 //
-// One CTA per distinct seed walks the stream block by block (624 words): the twist of a block
-// has three dependent sub-steps of 227 / 227 / 170 independent words, separated by
-// __syncthreads(); 312 doubles per block are tempered and written coalesced to every request of
-// that seed that overlaps the block.  Streams are independent, so seeds run on different SMs.
+// One CTA per distinct seed walks the stream block by block (624 words).  Word k of the new block
+// depends on new word k-227, so thread t produces words t, t+227, t+454 from the old block and
+// its own results: one __syncthreads() per block (state double-buffered in shared memory).  The
+// 312 doubles of a block are tempered and written coalesced to every request of that seed that
+// overlaps the block.  Streams are independent, so seeds run on different SMs.
 #include "common.cuh"
 #include <algorithm>
 #include <numeric>
@@ -64,39 +65,66 @@ __global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__re
 
     const uint64_t last_double = rq[job.n_req - 1].skip + static_cast<uint64_t>(rq[job.n_req - 1].count);
     const uint64_t n_blocks = (last_double + 311) / 312;   // blocks of 312 doubles to generate
-    int r0 = 0;                                            // first request not entirely before this block
+    // current request, cached in registers (all threads walk the request list in lock step)
+    int r0 = 0;
+    uint64_t r_beg = rq[0].skip, r_end = rq[0].skip + static_cast<uint64_t>(rq[0].count);
+    int64_t r_out = rq[0].out_off;
     int cur = 0;
     for (uint64_t blk = 0; blk < n_blocks; ++blk) {
         const uint32_t *o = s_mt[cur];
         uint32_t *nw = s_mt[cur ^ 1];
-        if (tid < 227) nw[tid] = o[tid + kMtM] ^ mt_mix(o[tid], o[tid + 1]);
-        __syncthreads();
-        if (tid < 227) nw[tid + 227] = nw[tid] ^ mt_mix(o[tid + 227], o[tid + 228]);
-        __syncthreads();
-        if (tid < 169) nw[tid + 454] = nw[tid + 227] ^ mt_mix(o[tid + 454], o[tid + 455]);
-        else if (tid == 169) nw[623] = nw[396] ^ mt_mix(o[623], nw[0]);
+        // The twist of word k needs the NEW word k-227, and 3 * 227 > 624: thread t produces words
+        // t, t+227 and t+454 from the old block and its own results, so one barrier per block is enough.
+        if (tid < 227) {
+            const uint32_t n0 = o[tid + kMtM] ^ mt_mix(o[tid], o[tid + 1]);
+            const uint32_t n1 = n0 ^ mt_mix(o[tid + 227], o[tid + 228]);
+            nw[tid] = n0;
+            nw[tid + 227] = n1;
+            if (tid < 169) {
+                nw[tid + 454] = n1 ^ mt_mix(o[tid + 454], o[tid + 455]);
+            } else if (tid == 169) {   // word 623 wraps around to the new word 0 (recomputed here)
+                const uint32_t new0 = o[kMtM] ^ mt_mix(o[0], o[1]);
+                nw[623] = n1 ^ mt_mix(o[623], new0);
+            }
+        }
         __syncthreads();
         cur ^= 1;
 
         const uint64_t d0 = blk * 312;                     // first double of this block
-        while (r0 < job.n_req && rq[r0].skip + static_cast<uint64_t>(rq[r0].count) <= d0) ++r0;
-        if (r0 < job.n_req && rq[r0].skip < d0 + 312 && tid < 312) {
-            const uint64_t d = d0 + tid;
-            int r = r0;
-            while (r < job.n_req && rq[r].skip + static_cast<uint64_t>(rq[r].count) <= d) ++r;
-            if (r < job.n_req && d >= rq[r].skip) {
-                const uint32_t a = mt_temper(nw[2 * tid]) >> 5, b = mt_temper(nw[2 * tid + 1]) >> 6;
-                const double u = (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) / 9007199254740992.0;
-                out[rq[r].out_off + static_cast<int64_t>(d - rq[r].skip)] = u;
+        while (r0 < job.n_req && r_end <= d0) {
+            ++r0;
+            if (r0 < job.n_req) {
+                r_beg = rq[r0].skip;
+                r_end = r_beg + static_cast<uint64_t>(rq[r0].count);
+                r_out = rq[r0].out_off;
             }
         }
-        // no barrier needed here: the next twist writes the buffer that was last *read* before
-        // the third barrier above, and reads the buffer the output phase is reading.
+        if (r0 < job.n_req && r_beg < d0 + 312 && tid < 312) {
+            const uint64_t d = d0 + tid;
+            uint64_t b = r_beg, e = r_end;
+            int64_t oo = r_out;
+            int r = r0;
+            while (r < job.n_req && e <= d) {              // rare: the block spans a request boundary
+                ++r;
+                if (r < job.n_req) {
+                    b = rq[r].skip;
+                    e = b + static_cast<uint64_t>(rq[r].count);
+                    oo = rq[r].out_off;
+                }
+            }
+            if (r < job.n_req && d >= b) {
+                const uint32_t a = mt_temper(nw[2 * tid]) >> 5, c = mt_temper(nw[2 * tid + 1]) >> 6;
+                const double u = (static_cast<double>(a) * 67108864.0 + static_cast<double>(c)) * (1.0 / 9007199254740992.0);   // exact: 2^-53
+                out[oo + static_cast<int64_t>(d - b)] = u;
+            }
+        }
+        // no second barrier: the next twist writes the buffer whose last readers passed the barrier
+        // above, and only reads the buffer this output phase reads.
     }
 }
 
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off, int n,
-             double *u_dev)
+             double *u_dev, cudaStream_t launch_on)
 {
     if (n == 0) return SSFE_OK;
     // group requests by seed, each group ordered by stream position
@@ -136,8 +164,18 @@ int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const i
     RandJob *d_jobs = upload(ctx, jobs.data(), jobs.size());
     RandReq *d_reqs = upload(ctx, reqs.data(), reqs.size());
     if (!d_jobs || !d_reqs) return SSFE_ERR_NOMEM;
-    mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, ctx->stream>>>(d_jobs, d_reqs, u_dev);
+    cudaStream_t st = launch_on ? launch_on : ctx->stream;
+    if (st != ctx->stream) {   // fork: the side stream sees the metadata and everything before it
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        SSFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+        if (ctx->timing) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_aux0, st));
+    }
+    mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, st>>>(d_jobs, d_reqs, u_dev);
     SSFE_LAUNCHED(ctx);
+    if (st != ctx->stream) {
+        if (ctx->timing) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_aux1, st));
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_join, st));
+    }
     return SSFE_OK;
 }
 

@@ -88,22 +88,33 @@ struct RaptParams {
 };
 
 // ---- K1 ------------------------------------------------------------------------------------
-__global__ void rapt_decimate_kernel(const RaptParams p)
+// 256 consecutive 2 kHz outputs of one utterance per CTA (n_ds is padded to a multiple of 256).  The
+// 2121 input samples are staged once, scaled by 32768, in shared memory with one pad word per 32 so
+// that the stride-8 tap reads of a warp fall in distinct banks.
+constexpr int kDecTile = 256;
+constexpr int kDecIn = kDec * (kDecTile - 1) + kNco;          // 2121
+__device__ __forceinline__ int dec_skew(int i) { return i + (i >> 5); }
+
+__global__ void __launch_bounds__(kDecTile) rapt_decimate_kernel(const RaptParams p)
 {
-    const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (gid >= p.total_ds) return;
-    const int u = find_segment(p.ds_offs, p.n, gid);
+    __shared__ float s_x[kDecIn + kDecIn / 32 + 2];
+    const long long gid0 = blockIdx.x * static_cast<long long>(kDecTile);
+    const int u = find_segment(p.ds_offs, p.n, gid0);
     const RaptUtt ut = p.utts[u];
-    const int m = static_cast<int>(gid - ut.ds_off);
+    const int m0 = static_cast<int>(gid0 - ut.ds_off);
     const float *x = p.wav + ut.wav_off;
+    const int base = kDec * m0 - (kNco / 2);
+    for (int i = threadIdx.x; i < kDecIn; i += kDecTile) {
+        const int idx = base + i;
+        s_x[dec_skew(i)] = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+    }
+    __syncthreads();
+    const int t8 = kDec * threadIdx.x;
     float sum = 0.0f;
 #pragma unroll 9
-    for (int j = 0; j < kNco; ++j) {
-        const int idx = kDec * m + j - (kNco / 2);
-        const float v = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
-        sum += c_rapt.co[j] * v;
-    }
-    p.ds[gid] = static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
+    for (int j = 0; j < kNco; ++j) sum += c_rapt.co[j] * s_x[dec_skew(t8 + j)];
+    p.ds[gid0 + threadIdx.x] =
+        static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
 }
 
 // ---- warp helpers ----------------------------------------------------------------------------
@@ -405,97 +416,139 @@ __device__ __forceinline__ void durbin18(const float *r, float *a_out, float *er
     *err = e;
 }
 
-constexpr int kStatWarps = 4;
+// One THREAD per 30 ms window.  The 19 autocorrelation chains (lags 0..18) of a window all consume
+// the same samples, so a thread keeps a sliding window of 19 pre-emphasised, Hanning-weighted samples
+// in registers and feeds 19 accumulators from it: one shared-memory read per 19 multiply-adds,
+// instead of two per multiply-add when a lane owns a single lag.  Every chain is still summed left to
+// right by one thread, so the result is bit-identical to the serial original.
+// A CTA covers 64 consecutive frames of one utterance: threads 0..63 take the current windows
+// (x + 256 g - 80), threads 64..127 the previous ones (x + 256 g - 400); the signal span is staged once
+// in shared memory (scaled by 32768, one pad word per 256 samples -> conflict-free column reads).
+constexpr int kStatFrames = 64;
+constexpr int kStatSpan = kHop * (kStatFrames - 1) + kStatGap + kStatW;      // 16928 samples
+__device__ __forceinline__ int stat_skew(int i) { return i + (i >> 8); }
 
-__global__ void __launch_bounds__(kStatWarps * 32) rapt_stat_kernel(const RaptParams p)
+__global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptParams p, const int *__restrict__ tile_off)
 {
-    __shared__ float s_w479[kStatW], s_w480[kStatW];
-    __shared__ float s_d[kStatWarps][kStatW];
-    __shared__ float s_r[kStatWarps][2][kLpcOrd + 2];   // stabilised autocorrelation: [0]=cur [1]=prev
-    __shared__ float s_a[kStatWarps][kLpcOrd + 2];
-    __shared__ float s_b[kStatWarps][kLpcOrd + 2];
-    for (int t = threadIdx.x; t < kStatW; t += blockDim.x) {
-        s_w479[t] = (t < kStatW - 1) ? p.w479[t] : 0.0f;
-        s_w480[t] = p.w480[t];
+    extern __shared__ float s_stat[];
+    float *s_x = s_stat;                                   // [kStatSpan + kStatSpan/256 + 1]
+    float *s_w479 = s_x + kStatSpan + kStatSpan / 256 + 2; // [480]
+    float *s_w480 = s_w479 + kStatW;                       // [480]
+    float *s_ex = s_w480 + kStatW;                         // [64][20]: rho1[1..18], err1, rms1 of the previous window
+
+    const int tid = threadIdx.x;
+    const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));
+    const RaptUtt ut = p.utts[u];
+    const int g0 = (static_cast<int>(blockIdx.x) - tile_off[u]) * kStatFrames;
+    const float *x = p.wav + ut.wav_off;
+    const int s_lo = kHop * g0 - (kStatGap + 80);
+    for (int i = tid; i < kStatSpan; i += 2 * kStatFrames) {
+        const int idx = s_lo + i;
+        s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+    }
+    for (int i = tid; i < kStatW; i += 2 * kStatFrames) {
+        s_w479[i] = (i < kStatW - 1) ? p.w479[i] : 0.0f;
+        s_w480[i] = p.w480[i];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long gf = blockIdx.x * static_cast<long long>(kStatWarps) + w;
-    if (gf >= p.total_fr) return;
-    const int u = find_segment(p.fr_offs, p.n, gf);
-    const RaptUtt ut = p.utts[u];
-    const int g = static_cast<int>(gf - ut.fr_off);
-    if (g < 2) {
-        if (lane == 0) {
-            p.sta[gf] = (g == 0) ? (0.01f * 0.2f) : static_cast<float>(0.2 / 10.0f);
-            p.rr[gf] = 1.0f;
-        }
-        return;
-    }
-    const float *x = p.wav + ut.wav_off;
-    float *d = s_d[w];
-    float rms[2] = {0.0f, 0.0f};
-    const int wsize = kStatW - 1;
-    for (int which = 0; which < 2; ++which) {
-        const float *win = x + static_cast<long long>(g) * kHop - (which == 0 ? 80 : 400);
-        for (int t = lane; t < wsize; t += 32)
-            d[t] = s_w479[t] * ((win[t + 1] * 32768.0f) - (c_rapt.preemp * (win[t] * 32768.0f)));
-        __syncwarp();
-        float acc = 0.0f;
-        if (lane == 0) {
-            for (int j = 0; j < wsize; ++j) acc += d[j] * d[j];
-        } else if (lane <= kLpcOrd) {
-            for (int j = 0; j < wsize - lane; ++j) acc += d[j] * d[j + lane];
-        } else if (lane == kLpcOrd + 1) {
-            for (int j = 0; j < kStatW; ++j) {
-                const float f = s_w480[j] * (win[j] * 32768.0f);
-                acc += f * f;
+
+    const bool is_prev = tid >= kStatFrames;
+    const int fl = is_prev ? tid - kStatFrames : tid;      // local frame
+    const int g = g0 + fl;
+    const bool live = (g < ut.n_fr) && (g >= 2);
+    const int b = kHop * fl + (is_prev ? 0 : kStatGap);    // window start inside the staged span
+
+    float acc[kLpcOrd + 1];
+    float rms = 0.0f;
+    if (live) {
+        float v[kLpcOrd + 1];
+        float en = 0.0f;
+        float xi = s_x[stat_skew(b)];
+        // produce(i): windowed pre-emphasised sample d[i] (0 for i >= 479), energy term of sample i
+        auto produce = [&](int i) -> float {
+            float d = 0.0f;
+            if (i < kStatW) {
+                const float f = s_w480[i] * xi;
+                en += f * f;
+                if (i < kStatW - 1) {
+                    const float xn = s_x[stat_skew(b + i + 1)];
+                    d = s_w479[i] * (xn - (c_rapt.preemp * xi));
+                    xi = xn;
+                }
             }
-            acc = static_cast<float>(sqrt(static_cast<double>(acc / kStatW)));
+            return d;
+        };
+#pragma unroll
+        for (int k = 0; k <= kLpcOrd; ++k) {
+            v[k] = produce(k);
+            acc[k] = 0.0f;
         }
-        const float sum0 = __shfl_sync(0xffffffffu, acc, 0);
-        rms[which] = __shfl_sync(0xffffffffu, acc, kLpcOrd + 1);
-        float rv;
+        const int wsize = kStatW - 1;
+        for (int jb = 0; jb * (kLpcOrd + 1) < wsize; ++jb) {
+#pragma unroll
+            for (int r = 0; r <= kLpcOrd; ++r) {
+                const int j = jb * (kLpcOrd + 1) + r;
+                if (j < wsize) {
+                    const float dj = v[r];
+#pragma unroll
+                    for (int k = 0; k <= kLpcOrd; ++k) acc[k] += dj * v[(r + k) % (kLpcOrd + 1)];
+                    v[r] = produce(j + kLpcOrd + 1);
+                }
+            }
+        }
+        rms = static_cast<float>(sqrt(static_cast<double>(en / kStatW)));
+    }
+    float a_lpc[kLpcOrd], err = 0.0f;
+    float rho[kLpcOrd + 1];
+    if (live) {
+        const float sum0 = acc[0];
+        rho[0] = 1.0f;
         if (sum0 == 0.0f) {
-            rv = (lane == 0) ? 1.0f : 0.0f;
+#pragma unroll
+            for (int k = 1; k <= kLpcOrd; ++k) rho[k] = 0.0f;
         } else {
             const float inv = 1.0 / sum0;
-            rv = (lane == 0) ? 1.0f : c_rapt.ffact * (acc * inv);
-        }
-        if (lane <= kLpcOrd) s_r[w][which][lane] = rv;
-        __syncwarp();
-    }
-    float a2[kLpcOrd], a1[kLpcOrd], err3, err1;
-    durbin18(s_r[w][0], a2, &err3);
-    durbin18(s_r[w][1], a1, &err1);
-    if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < kLpcOrd; ++i) s_a[w][i] = a2[i];
+            for (int k = 1; k <= kLpcOrd; ++k) rho[k] = c_rapt.ffact * (acc[k] * inv);
+        }
+        durbin18(rho, a_lpc, &err);
+        if (is_prev) {
+            float *e = s_ex + fl * 20;
+#pragma unroll
+            for (int k = 1; k <= kLpcOrd; ++k) e[k - 1] = rho[k];
+            e[18] = err;
+            e[19] = rms;
+        }
     }
-    __syncwarp();
-    // b = autocorrelation of the current inverse filter (a_to_aca)
-    const float *a = s_a[w];
-    if (lane < kLpcOrd) {
-        const int i = lane + 1;
-        float s = a[i - 1];
-        for (int j = 0; j < kLpcOrd - i; ++j) s += (a[j] * a[j + i]);
-        s_b[w][lane] = 2. * s;
-    } else if (lane == kLpcOrd) {
-        float s = 1.;
-        for (int i = 0; i < kLpcOrd; ++i) s += a[i] * a[i];
-        s_b[w][kLpcOrd] = s;
+    __syncthreads();
+    if (is_prev || g >= ut.n_fr) return;
+    const long long gf = ut.fr_off + g;
+    if (g < 2) {
+        p.sta[gf] = (g == 0) ? (0.01f * 0.2f) : static_cast<float>(0.2 / 10.0f);
+        p.rr[gf] = 1.0f;
+        return;
     }
-    __syncwarp();
-    if (lane == 0) {
-        float s = s_b[w][kLpcOrd];
-        for (int i = 0; i < kLpcOrd; ++i) s += s_r[w][1][i + 1] * s_b[w][i];
-        const float t = (s / err1) - .8;
-        p.rr[gf] = (0.001 + rms[0]) / rms[1];
-        p.sta[gf] = static_cast<float>(0.2 / t);
+    // b = autocorrelation of the current inverse filter (a_to_aca), Itakura distance against the
+    // previous window's autocorrelation
+    const float *e = s_ex + fl * 20;
+    float s = 1.;
+#pragma unroll
+    for (int i = 0; i < kLpcOrd; ++i) s += a_lpc[i] * a_lpc[i];
+    float dist = s;
+#pragma unroll
+    for (int i = 1; i <= kLpcOrd; ++i) {
+        float q = a_lpc[i - 1];
+#pragma unroll
+        for (int j = 0; j < kLpcOrd - i; ++j) q += (a_lpc[j] * a_lpc[j + i]);
+        const float bi = 2. * q;
+        dist += e[i - 1] * bi;
     }
-    (void)a1;
-    (void)err3;
+    const float t = (dist / e[18]) - .8;
+    p.rr[gf] = (0.001 + rms) / e[19];
+    p.sta[gf] = static_cast<float>(0.2 / t);
 }
+
+constexpr size_t kStatSmem = (kStatSpan + kStatSpan / 256 + 2 + 2 * kStatW + kStatFrames * 20) * sizeof(float);
 
 // ---- K4 ------------------------------------------------------------------------------------
 constexpr int kDpWarps = 4;
@@ -711,6 +764,8 @@ int init_rapt(ssfe_ctx *ctx)
     SSFE_CUDA(ctx, cudaMemcpy(T->d_w479, w479.data(), kStatW * sizeof(float), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpy(T->d_w480, w480.data(), kStatW * sizeof(float), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_rapt, &h, sizeof(h)));
+    SSFE_CUDA(ctx, cudaFuncSetAttribute(rapt_stat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kStatSmem)));
     return SSFE_OK;
 }
 
@@ -754,7 +809,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         ut.nl = (rem < cf.pad) ? 0 : static_cast<int>((rem - cf.pad) / kHop);
         ut.n_fr = ut.R_last * cf.F + ut.nl;
         if (ut.n_fr > ut.n_out) return set_error(ctx, SSFE_ERR_INVALID, "utterance %d: frame count mismatch", i);
-        ut.n_ds = static_cast<int>(L / kDec) + 8;
+        ut.n_ds = (static_cast<int>(L / kDec) + 8 + kDecTile - 1) / kDecTile * kDecTile;
         ut.fr_off = fr;
         ut.ds_off = dsn;
         fr_offs[i] = fr;
@@ -764,6 +819,13 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     }
     fr_offs[n] = fr;
     ds_offs[n] = dsn;
+    std::vector<int> stat_tile_off(n + 1);
+    long long stat_tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        stat_tile_off[i] = static_cast<int>(stat_tiles);
+        stat_tiles += (utts[i].n_fr + kStatFrames - 1) / kStatFrames;
+    }
+    stat_tile_off[n] = static_cast<int>(stat_tiles);
 
     int rc;
     if ((rc = ensure(ctx, ctx->ws.rapt_ds, dsn * sizeof(float)))) return rc;
@@ -773,6 +835,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     RaptParams p;
     memset(&p, 0, sizeof(p));
     p.wav = wav_base;
+    const int *d_stat_tiles = upload(ctx, stat_tile_off.data(), n + 1);
+    if (!d_stat_tiles) return SSFE_ERR_NOMEM;
     p.utts = upload(ctx, utts.data(), n);
     p.fr_offs = upload(ctx, fr_offs.data(), n + 1);
     p.ds_offs = upload(ctx, ds_offs.data(), n + 1);
@@ -804,14 +868,14 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     T->last_rr = p.rr;
 
     cudaStream_t st = ctx->stream;
-    rapt_decimate_kernel<<<static_cast<unsigned>((dsn + 255) / 256), 256, 0, st>>>(p);
+    rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecTile, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     mark(ctx, ST_RAPT_CAND);
     if (fr > 0) {
         rapt_cand_kernel<<<static_cast<unsigned>((fr + kCandWarps - 1) / kCandWarps), kCandWarps * 32, 0, st>>>(p);
         SSFE_LAUNCHED(ctx);
         mark(ctx, ST_RAPT_STAT);
-        rapt_stat_kernel<<<static_cast<unsigned>((fr + kStatWarps - 1) / kStatWarps), kStatWarps * 32, 0, st>>>(p);
+        rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles);
         SSFE_LAUNCHED(ctx);
     } else {
         mark(ctx, ST_RAPT_STAT);
