@@ -78,8 +78,9 @@ const char *ssfe_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t ssfe_launch_count(const ssfe_ctx *ctx);
 
-/* In-stream CUDA-event timing of the stages of ssfe_extract (off by default).  ssfe_stage_ms waits
- * for the most recent timed ssfe_extract and writes the milliseconds of, in order: rand (MT19937),
+/* In-stream CUDA-event timing of the stages of ssfe_extract (off by default; no host sync per
+ * call).  ssfe_stage_ms waits for the most recent timed ssfe_extract and writes the milliseconds,
+ * averaged over the (up to 64) calls since ssfe_enable_timing(ctx, 1), of, in order: rand (MT19937),
  * filtfilt (+ dither combine), reflect edges, fused STFT-mel kernel, RAPT decimate, RAPT
  * candidates, RAPT stationarity, RAPT Viterbi, F0 normalise/quantise.  Returns the stage count. */
 int  ssfe_enable_timing(ssfe_ctx *ctx, int on);

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 
 static char g_create_error[512] = "";
 
@@ -80,9 +81,25 @@ void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
 void mark(ssfe_ctx *ctx, int boundary)
 {
     if (!ctx->timing || boundary < 0 || boundary > ST_COUNT) return;
-    if (!ctx->ev[boundary]) cudaEventCreate(&ctx->ev[boundary]);
-    cudaEventRecord(ctx->ev[boundary], ctx->stream);
-    if (boundary + 1 > ctx->n_ev) ctx->n_ev = boundary + 1;
+    if (boundary == 0) {
+        ctx->timed_calls++;
+        ctx->slot_marks = 0;
+    }
+    if (ctx->timed_calls == 0) return;
+    const int slot = static_cast<int>((ctx->timed_calls - 1) % ssfe_ctx::kTimeRing);
+    cudaEvent_t &e = ctx->ev[slot][boundary];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, ctx->stream);
+    ctx->slot_marks = boundary + 1;
+}
+
+void mark_aux(ssfe_ctx *ctx, int which, cudaStream_t st)
+{
+    if (!ctx->timing || ctx->timed_calls == 0) return;
+    const int slot = static_cast<int>((ctx->timed_calls - 1) % ssfe_ctx::kTimeRing);
+    cudaEvent_t &e = ctx->ev_auxr[slot][which];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, st);
 }
 
 }  // namespace ssfe
@@ -93,20 +110,35 @@ extern "C" int ssfe_enable_timing(ssfe_ctx *ctx, int on)
 {
     if (!ctx) return SSFE_ERR_INVALID;
     ctx->timing = on != 0;
-    ctx->n_ev = 0;
+    if (on) ctx->timed_calls = 0;
     return SSFE_OK;
 }
 
 extern "C" int ssfe_stage_ms(ssfe_ctx *ctx, float *ms_out, int n)
 {
     if (!ctx || !ms_out) return SSFE_ERR_INVALID;
-    if (ctx->n_ev < ST_COUNT + 1) return set_error(ctx, SSFE_ERR_INVALID, "no timed ssfe_extract call yet");
-    SSFE_CUDA(ctx, cudaEventSynchronize(ctx->ev[ST_COUNT]));
-    for (int i = 0; i < n && i < ST_COUNT; ++i)
-        SSFE_CUDA(ctx, cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
-    // the dither kernel runs on the side stream, overlapped with filtfilt: report its own duration
-    if (n > ST_RAND && cudaEventQuery(ctx->ev_aux1) == cudaSuccess)
-        cudaEventElapsedTime(&ms_out[ST_RAND], ctx->ev_aux0, ctx->ev_aux1);
+    if (ctx->timed_calls == 0 || ctx->slot_marks < ST_COUNT + 1)
+        return set_error(ctx, SSFE_ERR_INVALID, "no timed ssfe_extract call yet");
+    const long long calls = std::min<long long>(ctx->timed_calls, ssfe_ctx::kTimeRing);
+    const int last = static_cast<int>((ctx->timed_calls - 1) % ssfe_ctx::kTimeRing);
+    SSFE_CUDA(ctx, cudaEventSynchronize(ctx->ev[last][ST_COUNT]));
+    for (int i = 0; i < n && i < ST_COUNT; ++i) ms_out[i] = 0.0f;
+    for (long long c = 0; c < calls; ++c) {
+        const int slot = static_cast<int>((ctx->timed_calls - 1 - c) % ssfe_ctx::kTimeRing);
+        for (int i = 0; i < n && i < ST_COUNT; ++i) {
+            float ms = 0.0f;
+            if (i == ST_RAND && ctx->ev_auxr[slot][0] && ctx->ev_auxr[slot][1] &&
+                cudaEventSynchronize(ctx->ev_auxr[slot][1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, ctx->ev_auxr[slot][0], ctx->ev_auxr[slot][1]) == cudaSuccess) {
+                ms_out[i] += ms;       // the dither kernel runs on the side stream: its own duration
+                continue;
+            }
+            SSFE_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[slot][i], ctx->ev[slot][i + 1]));
+            ms_out[i] += ms;
+        }
+    }
+    for (int i = 0; i < n && i < ST_COUNT; ++i) ms_out[i] /= static_cast<float>(calls);
+    cudaGetLastError();
     return ST_COUNT;
 }
 
@@ -162,6 +194,10 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
     ctx->device = device;
     ctx->cfg = *cfg;
     ctx->err[0] = 0;
+    if (const char *e = getenv("SSFE_HOST_CHUNK_SAMPLES")) {     // test hook: force many small sub-batches
+        const long long v = atoll(e);
+        if (v > 0) ctx->host_chunk_samples = v;
+    }
     ctx->mel_basis.assign(cfg->mel_basis, cfg->mel_basis + kBins * kMels);
     ctx->cfg.mel_basis = ctx->mel_basis.data();
     cudaDeviceProp prop;
@@ -176,8 +212,7 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
         if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
-        if ((e = cudaEventCreate(&ctx->ev_aux0)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
-        if ((e = cudaEventCreate(&ctx->ev_aux1)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_dith_free, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         ctx->stream = ctx->own_stream;
         if ((rc = init_stft_tables(ctx))) break;
         if ((rc = init_filtfilt(ctx))) break;
@@ -215,11 +250,20 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     if (ctx->meta_dev) cudaFree(ctx->meta_dev);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
-    for (cudaEvent_t e : ctx->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto &row : ctx->ev)
+        for (cudaEvent_t e : row)
+            if (e) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
-    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_aux0, ctx->ev_aux1})
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->aux_free[0], ctx->aux_free[1], ctx->ev_h2d[0],
+                          ctx->ev_h2d[1], ctx->ev_comp[0], ctx->ev_comp[1], ctx->ev_d2h[0], ctx->ev_d2h[1]})
         if (e) cudaEventDestroy(e);
+    for (auto &row : ctx->ev_auxr)
+        for (cudaEvent_t e : row)
+            if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->aux_host[i]) cudaFreeHost(ctx->aux_host[i]);
+        if (ctx->aux_dev[i]) cudaFree(ctx->aux_dev[i]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -317,8 +361,10 @@ extern "C" int ssfe_rapt(ssfe_ctx *ctx, const float *wav_dev, const int64_t *off
 
 // ---- the whole hot loop (make_spect_f0.py:50-74) ----------------------------------------------
 namespace ssfe {
+// dith_pre: raw dither words already being generated for exactly this batch's fixed offsets (the
+// caller ran rand_run on the side stream); nullptr = generate here.
 int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dtype, const ssfe_outputs *o,
-                   const std::vector<int64_t> &fix, const std::vector<int64_t> &foff)
+                   const std::vector<int64_t> &fix, const std::vector<int64_t> &foff, double *dith_pre = nullptr)
 {
     const int n = b->n_utts;
     // padded segment layout of the dithered wav
@@ -338,14 +384,14 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     int rc;
     if ((rc = check_ranges(ctx, b->f0_lo, b->f0_hi, n))) return rc;
     if ((rc = ensure(ctx, ctx->ws.wavp, (pos + kSegSlack) * sizeof(float)))) return rc;
-    if ((rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
+    if (!dith_pre && (rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
     float *wavp = static_cast<float *>(ctx->ws.wavp.p);
-    double *dith = static_cast<double *>(ctx->ws.dith.p);
+    double *dith = dith_pre ? dith_pre : static_cast<double *>(ctx->ws.dith.p);
 
     // the dither stream is independent of the signal until the very last filtfilt kernel: generate
     // it on a side stream while the forward / backward-local passes run
     mark(ctx, ST_RAND);
-    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
+    if (!dith_pre && (rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
     mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
@@ -357,6 +403,8 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     fo.wav = o->wav;
     fo.wav64 = o->wav64;
     fo.dith_ready = ctx->ev_join;
+    fo.dith_raw = true;
+    fo.keep_dith = dith_pre != nullptr;     // the caller releases the shared dither buffer after its last chunk
     if ((rc = filtfilt_run(ctx, x_dev, dtype, b->sample_offsets, fix.data(), n, fo))) return rc;
     mark(ctx, ST_EDGES);
     if ((rc = fill_reflect_edges(ctx, wavp, d_seg, d_fix, n))) return rc;
@@ -398,6 +446,11 @@ extern "C" int ssfe_extract(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_de
     return extract_device(ctx, b, x_dev, dtype, o, fix, foff);
 }
 
+// Host buffers in and out.  The batch is cut into sub-batches of ~64 M samples that flow through three
+// streams - H2D of sub-batch c+1, the kernels of sub-batch c and D2H of sub-batch c-1 overlap (input
+// and output slots are double buffered).  The dither streams of ALL sub-batches are generated once,
+// up front, on the side stream: a speaker's MT19937 stream is sequential, so regenerating it per
+// sub-batch would repeat the walk from the seed every time.
 extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_host, int dtype, float *mel_host,
                                  float *f0_norm_host, int64_t *bins_host)
 {
@@ -411,29 +464,102 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     const size_t esz = dtype == SSFE_F64 ? 8 : dtype == SSFE_F32 ? 4 : 2;
     std::vector<int64_t> fix(n + 1), foff(n + 1);
     ssfe_plan_offsets(b->sample_offsets, n, fix.data(), foff.data());
-    const int64_t total_in = b->sample_offsets[n] - b->sample_offsets[0];
-    const int64_t total_fr = foff[n];
-    if ((rc = ensure(ctx, ctx->h_x, total_in * esz))) return rc;
-    if ((rc = ensure(ctx, ctx->h_mel, total_fr * kMels * sizeof(float)))) return rc;
-    if ((rc = ensure(ctx, ctx->h_f0, total_fr * sizeof(float)))) return rc;
-    if (bins_host && (rc = ensure(ctx, ctx->h_bins, total_fr * sizeof(int64_t)))) return rc;
-    // offsets relative to the first sample of the batch
-    std::vector<int64_t> rel(n + 1);
-    for (int i = 0; i <= n; ++i) rel[i] = b->sample_offsets[i] - b->sample_offsets[0];
-    ssfe_batch rb = *b;
-    rb.sample_offsets = rel.data();
-    const char *src = static_cast<const char *>(x_host) + b->sample_offsets[0] * esz;
-    SSFE_CUDA(ctx, cudaMemcpyAsync(ctx->h_x.p, src, total_in * esz, cudaMemcpyHostToDevice, ctx->stream));
-    ssfe_outputs o;
-    memset(&o, 0, sizeof(o));
-    o.mel = static_cast<float *>(ctx->h_mel.p);
-    o.f0_norm = static_cast<float *>(ctx->h_f0.p);
-    o.bins = bins_host ? static_cast<int64_t *>(ctx->h_bins.p) : nullptr;
-    if ((rc = extract_device(ctx, &rb, ctx->h_x.p, dtype, &o, fix, foff))) return rc;
-    SSFE_CUDA(ctx, cudaMemcpyAsync(mel_host, o.mel, total_fr * kMels * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    SSFE_CUDA(ctx, cudaMemcpyAsync(f0_norm_host, o.f0_norm, total_fr * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (bins_host)
-        SSFE_CUDA(ctx, cudaMemcpyAsync(bins_host, o.bins, total_fr * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+
+    // sub-batches: cut at ~kChunkSamples, preferably where the speaker changes
+    const int64_t kChunkSamples = ctx->host_chunk_samples;
+    std::vector<int> cuts{0};
+    {
+        int start = 0;
+        while (start < n) {
+            int end = start;
+            int64_t acc = 0;
+            while (end < n && (acc < kChunkSamples || end == start)) {
+                acc += b->sample_offsets[end + 1] - b->sample_offsets[end];
+                ++end;
+            }
+            // extend to the end of the current speaker if that is close (keeps stream requests contiguous)
+            int ext = end;
+            while (ext < n && b->spk_seed[ext] == b->spk_seed[end - 1] && ext - end < 64) ++ext;
+            if (ext == n || b->spk_seed[ext] != b->spk_seed[end - 1]) end = ext;
+            cuts.push_back(end);
+            start = end;
+        }
+    }
+    const int n_chunks = static_cast<int>(cuts.size()) - 1;
+    int64_t max_in = 0, max_fr = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        max_in = std::max(max_in, b->sample_offsets[cuts[c + 1]] - b->sample_offsets[cuts[c]]);
+        max_fr = std::max(max_fr, foff[cuts[c + 1]] - foff[cuts[c]]);
+    }
+    // double-buffered device slots: [x | mel | f0 | bins]
+    const size_t in_b = (max_in * esz + 255) / 256 * 256, mel_b = (max_fr * kMels * 4 + 255) / 256 * 256,
+                 f0_b = (max_fr * 4 + 255) / 256 * 256, bins_b = bins_host ? (max_fr * 8 + 255) / 256 * 256 : 0;
+    const size_t slot_b = in_b + mel_b + f0_b + bins_b;
+    if ((rc = ensure(ctx, ctx->h_x, 2 * slot_b))) return rc;
+    if ((rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
+    for (int i = 0; i < 2; ++i)
+        for (cudaEvent_t *e : {&ctx->ev_h2d[i], &ctx->ev_comp[i], &ctx->ev_d2h[i]})
+            if (!*e) SSFE_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+
+    // all dither streams, once, on the side stream
+    double *dith = static_cast<double *>(ctx->ws.dith.p);
+    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
+
+    // the copy streams must not run ahead of work already queued on the compute stream
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
+    SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_fork, 0));
+
+    const char *src = static_cast<const char *>(x_host);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int u0 = cuts[c], u1 = cuts[c + 1], m = u1 - u0, slot = c & 1;
+        char *base = static_cast<char *>(ctx->h_x.p) + slot * slot_b;
+        void *d_x = base;
+        float *d_mel = reinterpret_cast<float *>(base + in_b);
+        float *d_f0 = reinterpret_cast<float *>(base + in_b + mel_b);
+        int64_t *d_bins = bins_host ? reinterpret_cast<int64_t *>(base + in_b + mel_b + f0_b) : nullptr;
+        const int64_t s0 = b->sample_offsets[u0], ns = b->sample_offsets[u1] - s0;
+        const int64_t f0 = foff[u0], nf = foff[u1] - f0;
+
+        // H2D (slot free once the kernels of sub-batch c-2 are done with it)
+        if (c >= 2) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[slot], 0));
+        SSFE_CUDA(ctx, cudaMemcpyAsync(d_x, src + s0 * esz, ns * esz, cudaMemcpyHostToDevice, ctx->copy_in));
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_in));
+
+        // kernels (outputs of sub-batch c-2 must have left the slot)
+        SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+        if (c >= 2) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
+        std::vector<int64_t> rel(m + 1), cfix(m + 1), cfoff(m + 1);
+        for (int i = 0; i <= m; ++i) {
+            rel[i] = b->sample_offsets[u0 + i] - s0;
+            cfix[i] = fix[u0 + i] - fix[u0];
+            cfoff[i] = foff[u0 + i] - f0;
+        }
+        ssfe_batch cb;
+        cb.n_utts = m;
+        cb.sample_offsets = rel.data();
+        cb.f0_lo = b->f0_lo + u0;
+        cb.f0_hi = b->f0_hi + u0;
+        cb.spk_seed = b->spk_seed + u0;
+        cb.dither_skip = b->dither_skip + u0;
+        ssfe_outputs o;
+        memset(&o, 0, sizeof(o));
+        o.mel = d_mel;
+        o.f0_norm = d_f0;
+        o.bins = d_bins;
+        if ((rc = extract_device(ctx, &cb, d_x, dtype, &o, cfix, cfoff, dith + fix[u0]))) return rc;
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->stream));
+
+        // D2H
+        SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[slot], 0));
+        SSFE_CUDA(ctx, cudaMemcpyAsync(mel_host + f0 * kMels, d_mel, nf * kMels * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+        SSFE_CUDA(ctx, cudaMemcpyAsync(f0_norm_host + f0, d_f0, nf * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (bins_host)
+            SSFE_CUDA(ctx, cudaMemcpyAsync(bins_host + f0, d_bins, nf * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[slot], ctx->copy_out));
+    }
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, ctx->stream));   // the shared dither buffer may be refilled
+    SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SSFE_OK;
 }

@@ -32,10 +32,11 @@ struct Workspace {
 };
 
 struct MelTables {
-    int n_entries = 0;                 // E: entries per lane (padded)
-    int n_seg = 0;                     // segments per lane
-    int2 *ent = nullptr;               // [E][32] (bin index, weight bits); weight already * 0.5
-    int2 *seg = nullptr;               // [n_seg][32] (end entry, band or -1)
+    int n_groups = 0;                  // aligned 4-bin groups per lane (all slots)
+    int slot_end[3] = {0, 0, 0};       // cumulative group count per (slot)
+    float4 *w4 = nullptr;              // [n_groups][32] weights (already * 0.5)
+    int *k0 = nullptr;                 // [n_groups][32] first bin of the group
+    int *band = nullptr;               // [3][32] band of (slot, lane), -1 = none
 };
 
 struct RaptTables;                     // rapt.cu
@@ -48,7 +49,13 @@ struct ssfe_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // ssfe_extract_host pipeline
     cudaStream_t aux = nullptr;                               // the dither stream runs beside filtfilt
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux0 = nullptr, ev_aux1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_dith_free = nullptr;                       // recorded after the kernel that reads `dith`
+    char *aux_host[2] = {nullptr, nullptr}, *aux_dev[2] = {nullptr, nullptr};   // side-stream metadata staging
+    size_t aux_cap[2] = {0, 0};
+    cudaEvent_t aux_free[2] = {nullptr, nullptr};
+    int aux_idx = 0;
     ssfe_config cfg;
     std::vector<float> mel_basis;      // host copy (513 x 80)
     char err[512];
@@ -67,11 +74,15 @@ struct ssfe_ctx {
     // host staging for ssfe_extract_host
     // optional in-stream stage timing of ssfe_extract (ssfe_enable_timing / ssfe_stage_ms)
     bool timing = false;
-    cudaEvent_t ev[16] = {};
-    int n_ev = 0;
+    static constexpr int kTimeRing = 64;                      // timed calls kept
+    cudaEvent_t ev[kTimeRing][12] = {};                       // stage boundaries of each timed call
+    cudaEvent_t ev_auxr[kTimeRing][2] = {};                   // side-stream (dither) start / end
+    long long timed_calls = 0;                                // since ssfe_enable_timing(1)
+    int slot_marks = 0;
     void *pin_in = nullptr;  size_t pin_in_cap = 0;
     void *pin_out = nullptr; size_t pin_out_cap = 0;
     ssfe::DevBuf h_x, h_mel, h_f0, h_bins;
+    long long host_chunk_samples = 256LL << 20;               // sub-batch size of ssfe_extract_host
 };
 
 namespace ssfe {
@@ -81,6 +92,7 @@ int set_error(ssfe_ctx *ctx, int code, const char *fmt, ...);
 enum Stage { ST_RAND = 0, ST_FILTFILT, ST_EDGES, ST_STFT, ST_RAPT_DEC, ST_RAPT_CAND, ST_RAPT_STAT, ST_RAPT_DP,
              ST_POST, ST_COUNT };
 void mark(ssfe_ctx *ctx, int boundary);     // records event `boundary` (0..ST_COUNT) when timing is on
+void mark_aux(ssfe_ctx *ctx, int which, cudaStream_t st);   // side-stream start (0) / end (1) of the current call
 int cuda_fail(ssfe_ctx *ctx, cudaError_t e, const char *what);
 int ensure(ssfe_ctx *ctx, DevBuf &b, size_t bytes);
 // copies `bytes` of host metadata to the device through the pinned arena; returns device pointer
@@ -132,12 +144,14 @@ void free_filtfilt(ssfe_ctx *ctx);
 // backward pass and writes it (f32) into the padded layout / wav_out / wav64_out.
 struct FiltOut {
     double *y = nullptr;             // filtfilt output (may be null when fused outputs requested)
-    const double *dith = nullptr;    // uniform doubles U (fixed offsets); wav = y*0.96 + (U-0.5)*1e-6
+    const double *dith = nullptr;    // dither stream (fixed offsets); wav = y*0.96 + (U-0.5)*1e-6
+    bool dith_raw = false;           // dith holds raw MT19937 word pairs (mt_convert.cuh), not doubles
     float *wavp = nullptr;           // padded layout base
     const int64_t *seg_off_dev = nullptr;
     float *wav = nullptr;            // flat f32 [fixed offsets]
     double *wav64 = nullptr;
     cudaEvent_t dith_ready = nullptr; // waited on right before the kernel that reads `dith`
+    bool keep_dith = false;           // do not signal "dither buffer free" after this call
 };
 int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_off_host,
                  const int64_t *fix_off_host, int n, const FiltOut &out);

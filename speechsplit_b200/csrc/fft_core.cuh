@@ -21,6 +21,55 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 
 namespace ssfe {
 
+// Complex add / subtract.  On sm_100a these are the packed FP32 instructions (add.rn.f32x2 ->
+// SASS FADD2): one issue slot for both components.  The STFT kernel is issue bound, not FMA-pipe
+// bound, so halving the instruction count of the butterfly adds is worth ~15 % of the kernel.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+SSFE_HD float2 cadd(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+SSFE_HD float2 csub(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+// (a.x*s, a.y*s) and a*b + c component-wise
+SSFE_HD float2 cscale(float2 a, float s)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
+SSFE_HD float2 cfma_s(float2 a, float s, float2 c)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%6}; "
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+    return r;
+}
+SSFE_HD float2 cmul2(float2 a, float2 b)   // component-wise product
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+#else
+SSFE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+SSFE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+SSFE_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+SSFE_HD float2 cfma_s(float2 a, float s, float2 c) { return make_float2(a.x * s + c.x, a.y * s + c.y); }
+SSFE_HD float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
+
 // cos(2*pi*p/32), sin(2*pi*p/32) for p = 0..8 (first quadrant incl. ends)
 SSFE_HD constexpr float cos32q(int p)
 {
@@ -71,8 +120,8 @@ SSFE_HD void fft32_dif(float2 (&v)[32])
 #pragma unroll
             for (int i = 0; i < span / 2; ++i) {
                 const float2 a = v[base + i], b = v[base + i + span / 2];
-                v[base + i] = make_float2(a.x + b.x, a.y + b.y);
-                v[base + i + span / 2] = mul_w32(make_float2(a.x - b.x, a.y - b.y), i * (32 / span));
+                v[base + i] = cadd(a, b);
+                v[base + i + span / 2] = mul_w32(csub(a, b), i * (32 / span));
             }
         }
     }

@@ -22,6 +22,7 @@
 // round-off (measured against exact arithmetic); the scan agrees with it to that level.
 // filtfilt_mode 1 runs one thread per utterance (chunk = whole signal): a validation aid.
 #include "common.cuh"
+#include "mt_convert.cuh"
 #include <algorithm>
 
 namespace ssfe {
@@ -54,6 +55,7 @@ struct FiltParams {
     float *wav;
     double *wav64;
     double *y1_out;               // forward pass output (extended)
+    int dith_raw;                 // dith holds raw MT19937 word pairs
 };
 
 __constant__ FiltConsts c_filt;
@@ -140,7 +142,9 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
                 if (nidx >= 0 && nidx < Lf) {
                     if (p.y) p.y[fbase + nidx] = y;
                     if (p.dith) {
-                        const double d = __dmul_rn(__dsub_rn(p.dith[fbase + nidx], 0.5), c_filt.dither_scale);
+                        const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(p.dith)[fbase + nidx])
+                                                     : p.dith[fbase + nidx];
+                        const double d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
                         const double w = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
                         if (p.wav64) p.wav64[fbase + nidx] = w;
                         const float wf = static_cast<float>(w);
@@ -154,6 +158,153 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
     if (!FINAL) {
         double *s = p.state + static_cast<int64_t>(g) * 5;
         s[0] = f.z0; s[1] = f.z1; s[2] = f.z2; s[3] = f.z3; s[4] = f.z4;
+    }
+}
+
+// ---- warp-tiled version of the chunk kernel (the production path) ---------------------------------
+// A thread walking its own 256-sample chunk touches a different cache line than its 31 neighbours on
+// every load and store (32 L1 wavefronts per instruction).  Here a warp owns 32 CONSECUTIVE chunks of
+// one utterance (8192 contiguous samples) and moves them through a shared-memory tile 32 samples at
+// a time: global traffic is row-wise and fully coalesced (PCM decode, odd extension, dither combine
+// and the f32 scatter happen on that side), the recurrence reads and writes the tile column-wise.
+constexpr int kTileW = 32;                   // samples per row and sub-step
+constexpr int kTileStride = kTileW + 1;      // doubles per tile row (column reads are conflict-free)
+constexpr int kFiltWarps = 4;
+
+// the local pass only feeds the carry, so it may use fused multiply-adds (11 instead of 21 fp64 ops)
+struct Df2tFused {
+    double z0, z1, z2, z3, z4;
+    __device__ __forceinline__ void step(double x)
+    {
+        const FiltConsts &c = c_filt;
+        const double y = fma(c.b[0], x, z0);
+        z0 = fma(-c.a[1], y, fma(c.b[1], x, z1));
+        z1 = fma(-c.a[2], y, fma(c.b[2], x, z2));
+        z2 = fma(-c.a[3], y, fma(c.b[3], x, z3));
+        z3 = fma(-c.a[4], y, fma(c.b[4], x, z4));
+        z4 = fma(-c.a[5], y, c.b[5] * x);
+    }
+};
+
+template <int DTYPE, int PASS, bool FINAL>
+__global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
+                                                                     int n_tiles)
+{
+    __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tile = blockIdx.x * kFiltWarps + w;
+    if (tile >= n_tiles) return;
+    double *tl = s_tile[w];
+    const int u = find_segment(tile_off, p.n, tile);
+    const int sc = tile - tile_off[u];                         // super-chunk (32 chunks) inside the utterance
+    const int nch = p.chunk_off[u + 1] - p.chunk_off[u];
+    const int c = sc * 32 + lane;                              // this lane's chunk
+    const int64_t xbase = p.in_off[u];
+    const int64_t fbase = p.fix_off[u];
+    // positions inside one utterance fit 32 bits (checked on the host); 64-bit only for the bases
+    const int L = static_cast<int>(p.in_off[u + 1] - xbase);
+    const int Lf = static_cast<int>(p.fix_off[u + 1] - fbase);
+    const int M = Lf + 2 * kPadLen;
+    const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
+    const int jt = sc * 32 * kChunk;                           // first sample of the super-chunk
+    const int rows = min(32, nch - sc * 32);                   // chunks present in this tile
+    const bool have = c < nch;
+    const int j0 = c * kChunk;
+    const bool last_chunk = have && (j0 + kChunk >= M);
+    const bool run = have && (FINAL || !last_chunk);           // nobody consumes the carry of the last chunk
+    const int64_t g = static_cast<int64_t>(p.chunk_off[u]) + c;
+
+    Df2t f;
+    Df2tFused ff;
+    if (FINAL) {
+        if (have) {
+            const double *s = p.state + g * 5;
+            f.z0 = s[0]; f.z1 = s[1]; f.z2 = s[2]; f.z3 = s[3]; f.z4 = s[4];
+        }
+    } else {
+        ff.z0 = ff.z1 = ff.z2 = ff.z3 = ff.z4 = 0.0;
+    }
+    const double *y1 = p.y1 + ebase;
+    double *y1o = FINAL ? p.y1_out + ebase : nullptr;
+    const double *dith = (FINAL && PASS == 1 && p.dith) ? p.dith + fbase : nullptr;
+    float *wavp = (FINAL && PASS == 1 && p.wavp) ? p.wavp + p.seg_off[u] + kHalfPad : nullptr;
+    for (int sub = 0; sub < kChunk / kTileW; ++sub) {
+        // ---- load: row r = chunk sc*32+r, column = lane -----------------------------------------
+        // (the kernel is bound by global-memory latency: on full tiles 16 independent loads are kept
+        // in flight per thread)
+        auto load_row = [&](int r) -> double {
+            const int jr = jt + r * kChunk + sub * kTileW;     // first sample of this row segment
+            const int j = jr + lane;
+            double v = 0.0;
+            if (PASS == 0) {
+                if (jr >= kPadLen && jr + kTileW <= kPadLen + L) {          // interior: plain samples
+                    v = load_sample<DTYPE>(p.x, xbase + (j - kPadLen));
+                } else if (j < M) {
+                    v = ext_sample<DTYPE>(p.x, xbase, L, Lf, j);
+                }
+            } else if (j < M) {
+                v = y1[M - 1 - j];
+            }
+            return v;
+        };
+        if (rows == 32) {
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 16) {
+                double tmp[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) tmp[q] = load_row(r0 + q);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) tl[(r0 + q) * kTileStride + lane] = tmp[q];
+            }
+        } else {
+            for (int r = 0; r < rows; ++r) tl[r * kTileStride + lane] = load_row(r);
+        }
+        __syncwarp();
+        // ---- recurrence: this lane's chunk is row `lane` -------------------------------------------
+        if (run) {
+            const int left = M - (j0 + sub * kTileW);                        // may be <= 0 past the end
+            const int cnt = left < kTileW ? left : kTileW;
+            double *row = tl + lane * kTileStride;
+            if (FINAL) {
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) row[i] = f.step(row[i]);
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) ff.step(row[i]);
+            }
+        }
+        __syncwarp();
+        // ---- store (final passes): row-wise again ---------------------------------------------------
+        if (FINAL) {
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                const int j = jt + r * kChunk + sub * kTileW + lane;
+                if (j >= M) continue;
+                const double y = tl[r * kTileStride + lane];
+                if (PASS == 0) {
+                    y1o[j] = y;
+                } else {
+                    const int nidx = M - 1 - kPadLen - j;
+                    if (nidx >= 0 && nidx < Lf) {
+                        if (p.y) p.y[fbase + nidx] = y;
+                        if (dith) {
+                            const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(dith)[nidx]) : dith[nidx];
+                            const double d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
+                            const double wv = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
+                            if (p.wav64) p.wav64[fbase + nidx] = wv;
+                            const float wf = static_cast<float>(wv);
+                            if (p.wav) p.wav[fbase + nidx] = wf;
+                            if (wavp) wavp[nidx] = wf;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (!FINAL && run) {
+        double *s = p.state + g * 5;
+        s[0] = ff.z0; s[1] = ff.z1; s[2] = ff.z2; s[3] = ff.z3; s[4] = ff.z4;
     }
 }
 
@@ -257,29 +408,34 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 }
 
 template <int DTYPE>
-static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready)
+static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready, bool keep_dith,
+                          const int *tile_off, int n_tiles)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
+    const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
     const unsigned gu = (p.n + 63) / 64;
     cudaStream_t st = ctx->stream;
     if (!sequential) {
-        filt_chunk_kernel<DTYPE, 0, false><<<gc, kFiltThreads, 0, st>>>(p);
+        filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
         SSFE_LAUNCHED(ctx);
     }
     filt_carry_kernel<DTYPE, 0><<<gu, 64, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
-    filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
+    if (sequential) filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
+    else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
     SSFE_LAUNCHED(ctx);
     p.y1 = p.y1_out;
     if (!sequential) {
-        filt_chunk_kernel<DTYPE, 1, false><<<gc, kFiltThreads, 0, st>>>(p);
+        filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
         SSFE_LAUNCHED(ctx);
     }
     filt_carry_kernel<DTYPE, 1><<<gu, 64, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
-    filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
+    if (sequential) filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
+    else filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
     SSFE_LAUNCHED(ctx);
+    if (dith_ready && !keep_dith) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));   // the dither buffer may be refilled
     return SSFE_OK;
 }
 
@@ -288,20 +444,25 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
 {
     if (n == 0) return SSFE_OK;
     const bool sequential = ctx->cfg.filtfilt_mode == 1;
-    std::vector<int> chunk_off(n + 1);
-    int64_t chunks = 0, max_m = 0;
+    std::vector<int> chunk_off(n + 1), tile_off(n + 1);
+    int64_t chunks = 0, max_m = 0, tiles = 0;
     for (int i = 0; i < n; ++i) {
         const int64_t Lf = fix_off_host[i + 1] - fix_off_host[i];
         if (Lf <= kPadLen)
             return set_error(ctx, SSFE_ERR_TOO_SHORT,
                              "utterance %d: the length of the input vector x must be greater than padlen, which is 18", i);
         const int64_t M = Lf + 2 * kPadLen;
+        if (M > 0x3fffffff) return set_error(ctx, SSFE_ERR_INVALID, "utterance %d is too long (%lld samples)", i, (long long)Lf);
         max_m = std::max(max_m, M);
         chunk_off[i] = static_cast<int>(chunks);
-        chunks += sequential ? 1 : (M + kChunk - 1) / kChunk;
+        tile_off[i] = static_cast<int>(tiles);
+        const int64_t nc = sequential ? 1 : (M + kChunk - 1) / kChunk;
+        chunks += nc;
+        tiles += (nc + 31) / 32;
         if (chunks > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (chunks)");
     }
     chunk_off[n] = static_cast<int>(chunks);
+    tile_off[n] = static_cast<int>(tiles);
     const int64_t ext_total = fix_off_host[n] + static_cast<int64_t>(n) * 2 * kPadLen;
     int rc = ensure(ctx, ctx->ws.y1, ext_total * sizeof(double));
     if (rc) return rc;
@@ -315,22 +476,25 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.in_off = upload(ctx, in_off_host, n + 1);
     p.fix_off = upload(ctx, fix_off_host, n + 1);
     p.chunk_off = upload(ctx, chunk_off.data(), n + 1);
-    if (!p.in_off || !p.fix_off || !p.chunk_off) return SSFE_ERR_NOMEM;
+    const int *d_tile_off = upload(ctx, tile_off.data(), n + 1);
+    if (!p.in_off || !p.fix_off || !p.chunk_off || !d_tile_off) return SSFE_ERR_NOMEM;
+    const int n_tiles = static_cast<int>(tiles);
     p.n = n;
     p.n_chunks = static_cast<int>(chunks);
     p.chunk_len = sequential ? static_cast<int>(std::min<int64_t>(max_m, 0x7fffffff)) : kChunk;
     p.state = static_cast<double *>(ctx->ws.carry.p);
     p.y = out.y;
     p.dith = out.dith;
+    p.dith_raw = out.dith_raw ? 1 : 0;
     p.wavp = out.wavp;
     p.seg_off = out.seg_off_dev;
     p.wav = out.wav;
     p.wav64 = out.wav64;
     p.y1_out = static_cast<double *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }

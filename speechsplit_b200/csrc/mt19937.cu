@@ -11,6 +11,7 @@
 // 312 doubles of a block are tempered and written coalesced to every request of that seed that
 // overlaps the block.  Streams are independent, so seeds run on different SMs.
 #include "common.cuh"
+#include "mt_convert.cuh"
 #include <algorithm>
 #include <numeric>
 
@@ -35,18 +36,9 @@ __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
-{
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
-}
-
 __global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__restrict__ jobs,
                                                              const RandReq *__restrict__ reqs,
-                                                             double *__restrict__ out)
+                                                             uint2 *__restrict__ out)
 {
     __shared__ uint32_t s_mt[2][kMtN];
     const RandJob job = jobs[blockIdx.x];
@@ -112,15 +104,20 @@ __global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__re
                     oo = rq[r].out_off;
                 }
             }
-            if (r < job.n_req && d >= b) {
-                const uint32_t a = mt_temper(nw[2 * tid]) >> 5, c = mt_temper(nw[2 * tid + 1]) >> 6;
-                const double u = (static_cast<double>(a) * 67108864.0 + static_cast<double>(c)) * (1.0 / 9007199254740992.0);   // exact: 2^-53
-                out[oo + static_cast<int64_t>(d - b)] = u;
-            }
+            if (r < job.n_req && d >= b)     // raw word pair; tempering + conversion happen in the consumer
+                out[oo + static_cast<int64_t>(d - b)] = *reinterpret_cast<const uint2 *>(nw + 2 * tid);
         }
         // no second barrier: the next twist writes the buffer whose last readers passed the barrier
         // above, and only reads the buffer this output phase reads.
     }
+}
+
+__global__ void mt_convert_kernel(double *__restrict__ u, int64_t count)
+{
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= count) return;
+    const uint2 raw = reinterpret_cast<const uint2 *>(u)[i];
+    u[i] = mt_raw_to_double(raw);
 }
 
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off, int n,
@@ -161,21 +158,49 @@ int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const i
         jobs.back().n_req++;
     }
     if (jobs.empty()) return SSFE_OK;
-    RandJob *d_jobs = upload(ctx, jobs.data(), jobs.size());
-    RandReq *d_reqs = upload(ctx, reqs.data(), reqs.size());
-    if (!d_jobs || !d_reqs) return SSFE_ERR_NOMEM;
-    cudaStream_t st = launch_on ? launch_on : ctx->stream;
-    if (st != ctx->stream) {   // fork: the side stream sees the metadata and everything before it
-        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        SSFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
-        if (ctx->timing) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_aux0, st));
+    if (launch_on == nullptr || launch_on == ctx->stream) {
+        // public ssfe_rand path: everything on the caller's stream, doubles out
+        RandJob *d_jobs = upload(ctx, jobs.data(), jobs.size());
+        RandReq *d_reqs = upload(ctx, reqs.data(), reqs.size());
+        if (!d_jobs || !d_reqs) return SSFE_ERR_NOMEM;
+        mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, ctx->stream>>>(
+            d_jobs, d_reqs, reinterpret_cast<uint2 *>(u_dev));
+        SSFE_LAUNCHED(ctx);
+        const int64_t total = out_off[n];
+        mt_convert_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(u_dev, total);
+        SSFE_LAUNCHED(ctx);
+        return SSFE_OK;
     }
-    mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, st>>>(d_jobs, d_reqs, u_dev);
+    // pipeline path: the generator runs on the side stream and leaves RAW word pairs.  It only has to
+    // wait for the previous consumer of the dither buffer (ev_dith_free), not for the rest of the
+    // previous ssfe_extract call, so in a stream of calls it overlaps the previous call's STFT / RAPT.
+    // Its metadata therefore travels on the side stream too, through its own double-buffered staging.
+    cudaStream_t st = launch_on;
+    const size_t jb = jobs.size() * sizeof(RandJob), rb = reqs.size() * sizeof(RandReq);
+    const size_t need = (jb + 255) / 256 * 256 + rb;
+    const int slot = ctx->aux_idx ^= 1;
+    if (ctx->aux_free[slot]) SSFE_CUDA(ctx, cudaEventSynchronize(ctx->aux_free[slot]));   // two calls back
+    else SSFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_free[slot], cudaEventDisableTiming));
+    if (need > ctx->aux_cap[slot]) {
+        if (ctx->aux_host[slot]) cudaFreeHost(ctx->aux_host[slot]);
+        if (ctx->aux_dev[slot]) cudaFree(ctx->aux_dev[slot]);
+        ctx->aux_cap[slot] = need + need / 4 + 4096;
+        SSFE_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->aux_host[slot]), ctx->aux_cap[slot]));
+        SSFE_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->aux_dev[slot]), ctx->aux_cap[slot]));
+    }
+    char *h = ctx->aux_host[slot], *d = ctx->aux_dev[slot];
+    memcpy(h, jobs.data(), jb);
+    memcpy(h + (jb + 255) / 256 * 256, reqs.data(), rb);
+    SSFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_dith_free, 0));
+    SSFE_CUDA(ctx, cudaMemcpyAsync(d, h, need, cudaMemcpyHostToDevice, st));
+    mark_aux(ctx, 0, st);
+    mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, st>>>(
+        reinterpret_cast<const RandJob *>(d), reinterpret_cast<const RandReq *>(d + (jb + 255) / 256 * 256),
+        reinterpret_cast<uint2 *>(u_dev));
     SSFE_LAUNCHED(ctx);
-    if (st != ctx->stream) {
-        if (ctx->timing) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_aux1, st));
-        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_join, st));
-    }
+    mark_aux(ctx, 1, st);
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_join, st));
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->aux_free[slot], st));
     return SSFE_OK;
 }
 

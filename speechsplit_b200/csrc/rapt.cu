@@ -255,14 +255,19 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
                 for (int j = 0; j < size; ++j) dot0 += db[j] * db[lane + start + j];
             if (lane + 32 < nlags)
                 for (int j = 0; j < size; ++j) dot1 += db[j] * db[lane + 32 + start + j];
+            // the lagged energy is a running (sequential, double) update; every lane walks the chain
+            // but only keeps the values of its own lags - the square root and the division, the
+            // expensive part, are then done once per lag instead of once per step
+            double e0 = engc, e1 = engc;
             for (int k = 0; k < nlags; ++k) {
-                const double den = sqrt(engc * engr);
-                if (k == lane) t0 = dot0 / den;
-                if (k == lane + 32) t1 = dot1 / den;
+                if (k == lane) e0 = engc;
+                if (k == lane + 32) e1 = engc;
                 const float a0 = db[k + start], az = db[k + start + size];
                 engc -= static_cast<double>(a0 * a0);
                 if ((engc += static_cast<double>(az * az)) < 1.0) engc = 1.0;
             }
+            if (lane < nlags) t0 = dot0 / sqrt(e0 * engr);
+            if (lane + 32 < nlags) t1 = dot1 / sqrt(e1 * engr);
         }
         if (lane < nlags) cc[lane] = t0;
         if (lane + 32 < nlags) cc[lane + 32] = t1;
@@ -304,54 +309,54 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
         __syncwarp();
         for (int t = lane; t < total; t += 32) db[t] = db[t] - engr;
         __syncwarp();
-        float sum = 0.0f;
-        for (int j = 0; j < kWin; ++j) { const float st = db[j]; sum += st * st; }
-        engr = sum;
+        // window energies in ONE pass: lanes < ncand sum their candidate's first lagged window, lane 31
+        // sums the reference window (each still a single left-to-right float chain)
+        int my_st = 0;
+        if (lane < ncand) {
+            my_st = lc[lane] - 3;
+            if (my_st < start0) my_st = start0;
+            stc[lane] = my_st;
+        }
+        float s2 = 0.0f;
+        if (lane < ncand || lane == 31) {
+            const float *q = db + my_st;
+            for (int j = 0; j < kWin; ++j) { const float st = q[j]; s2 += st * st; }
+        }
+        engr = __shfl_sync(0xffffffffu, s2, 31);
         maxval = 0.0f;
         if (engr > 0.0f) {
-            if (lane < ncand) {
-                int st = lc[lane] - 3;
-                if (st < start0) st = start0;
-                stc[lane] = st;
-            }
-            __syncwarp();
+            float vmax = 0.0f;
             for (int wk = lane; wk < ncand * 7; wk += 32) {
                 const int c = wk / 7, t = wk - 7 * c;
                 const float *dsp = db + stc[c] + t;
                 float dot = 0.0f;
+#pragma unroll 8
                 for (int j = 0; j < kWin; ++j) dot += db[j] * dsp[j];
                 val[wk] = dot;
             }
             __syncwarp();
             if (lane < ncand) {
-                const int st = stc[lane];
-                float s2 = 0.0f;
-                for (int j = 0; j < kWin; ++j) { const float q = db[st + j]; s2 += q * q; }
+                const int st = my_st;
                 double engc = s2;
                 for (int t = 0; t < 7; ++t) {
                     if (engc < 1.0) engc = 1.0;
                     const float dot = val[lane * 7 + t];
-                    val[lane * 7 + t] = static_cast<float>(dot / sqrt(10000.0 + (engc * engr)));
+                    const float v = static_cast<float>(dot / sqrt(10000.0 + (engc * engr)));
+                    val[lane * 7 + t] = v;
+                    vmax = fmaxf(vmax, v);
                     const float a0 = db[st + t], az = db[st + t + kWin];
                     engc -= static_cast<double>(a0 * a0);
                     engc += static_cast<double>(az * az);
                 }
             }
             __syncwarp();
-            if (lane == 0) {   // windows are written in candidate order; later ones overwrite
-                float amax = 0.0f;
-                for (int c = 0; c < ncand; ++c) {
-                    const int o = stc[c] - start0;
-                    for (int t = 0; t < 7; ++t) {
-                        const float v = val[c * 7 + t];
-                        if (o + t < kCcMax) cc[o + t] = v;
-                        if (v > amax) amax = v;
-                    }
-                }
-                val[0] = amax;
+            // windows are written in candidate order; later ones overwrite earlier ones
+            for (int c = 0; c < ncand; ++c) {
+                const int o = stc[c] - start0 + lane;
+                if (lane < 7 && o < kCcMax) cc[o] = val[c * 7 + lane];
+                __syncwarp();
             }
-            __syncwarp();
-            maxval = val[0];
+            maxval = warp_max(vmax);       // max over every value computed (order independent)
         }
         __syncwarp();
         ncand = pick_candidates(cc, nlags0, start0, maxval, pk, lc, lane);
@@ -421,10 +426,10 @@ __device__ __forceinline__ void durbin18(const float *r, float *a_out, float *er
 // in registers and feeds 19 accumulators from it: one shared-memory read per 19 multiply-adds,
 // instead of two per multiply-add when a lane owns a single lag.  Every chain is still summed left to
 // right by one thread, so the result is bit-identical to the serial original.
-// A CTA covers 64 consecutive frames of one utterance: threads 0..63 take the current windows
-// (x + 256 g - 80), threads 64..127 the previous ones (x + 256 g - 400); the signal span is staged once
+// A CTA covers 32 consecutive frames of one utterance: warp 0 takes the current windows
+// (x + 256 g - 80), warp 1 the previous ones (x + 256 g - 400); the signal span is staged once
 // in shared memory (scaled by 32768, one pad word per 256 samples -> conflict-free column reads).
-constexpr int kStatFrames = 64;
+constexpr int kStatFrames = 32;
 constexpr int kStatSpan = kHop * (kStatFrames - 1) + kStatGap + kStatW;      // 16928 samples
 __device__ __forceinline__ int stat_skew(int i) { return i + (i >> 8); }
 
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     float *s_x = s_stat;                                   // [kStatSpan + kStatSpan/256 + 1]
     float *s_w479 = s_x + kStatSpan + kStatSpan / 256 + 2; // [480]
     float *s_w480 = s_w479 + kStatW;                       // [480]
-    float *s_ex = s_w480 + kStatW;                         // [64][20]: rho1[1..18], err1, rms1 of the previous window
+    float *s_ex = s_w480 + kStatW;                         // [frames][20]: rho1[1..18], err1, rms1 of the previous window
 
     const int tid = threadIdx.x;
     const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));

@@ -6,16 +6,23 @@
 //
 // Data layout in HBM: the dithered wav of utterance i lives in a *padded segment*
 //     [512 reflected | L_i samples | 512 reflected | slack]          (float32, 256 B aligned)
-// so frame t of utterance i is the contiguous run  seg_i + 256 t ... + 1024  and a tile of 8
-// consecutive frames is one contiguous 11 KiB run: it is staged with a single TMA bulk copy
-// (cp.async.bulk + mbarrier), double buffered so the copy of tile n+1 overlaps the FFTs of tile n.
+// so frame t of utterance i is the contiguous run  seg_i + 256 t ... + 1024, and a PAIR of adjacent
+// frames is one contiguous 5 KiB run.
 //
-// Work split: persistent CTAs of 4 warps; a warp transforms two adjacent frames with one complex
-// 1024-point FFT held in registers (fft_core.cuh); |X| of the 513 bins of both frames goes to
-// shared memory, and the 941 non-zero mel weights are applied from a per-lane entry list built at
-// ssfe_create so that every lane carries ~30 FMAs per frame.  Arithmetic is fp32 FMA on the CUDA
-// cores - no tensor cores (BASELINE.json north_star) - and the kernel is bound by FP32 issue, not
-// by HBM: 1344 algorithmic bytes per frame against ~900 warp instructions.
+// Work split (v2): one persistent CTA of 12 warps per SM; every warp is an independent pipeline over
+// frame pairs - no block-level barrier anywhere in the main loop:
+//   * its pair is staged with ONE TMA bulk copy (cp.async.bulk -> SASS UBLKCP) completing on the
+//     warp's own mbarrier.  The staged samples are only needed until they sit in registers (the
+//     first ~130 instructions of ~1300), so the copy for the warp's NEXT pair is issued right after
+//     that and lands while the FFT runs: a single 5 KiB stage buffer per warp is enough;
+//   * the two frames are the real and imaginary parts of one complex 1024-point FFT held in
+//     registers (fft_core.cuh, 32 x 32 Cooley-Tukey, transpose through shared memory); butterfly
+//     adds, window multiplies, the spectrum split and the mel FMAs use the packed FP32 instructions
+//     of sm_100a (FADD2 / FMUL2 / FFMA2): the kernel is bound by instruction issue, not by HBM;
+//   * |A[k]|, |B[k]| of the two frames are stored interleaved so one 128-bit shared-memory load
+//     feeds two bins of both frames; the 941 non-zero mel weights are grouped in aligned runs of 4
+//     bins, bands are dealt to (slot, lane) by size so the loop is uniform across the warp.
+// Arithmetic is fp32 on the CUDA cores - no tensor cores (BASELINE.json north_star).
 #include "common.cuh"
 #include "fft_core.cuh"
 #include <algorithm>
@@ -24,32 +31,32 @@
 
 namespace ssfe {
 
-constexpr int kTileFrames = 8;                              // frames per CTA iteration
-constexpr int kStageFloats = (kTileFrames + 3) * kHop;      // 2816 floats = 11264 B
-constexpr int kStftThreads = 128;
+constexpr int kStftWarps = 12;
+constexpr int kStftThreads = kStftWarps * 32;
+constexpr int kPairFloats = kNfft + kHop;                   // 1280 samples = 5120 B per frame pair
 constexpr int kWarpTrans = 32 * kTransStride;               // float2 per warp
-constexpr int kMaxEnt = 64;
-constexpr int kMaxSeg = 8;
+constexpr int kMaxGroups = 24;
+constexpr int kMelSlots = 3;
+
+struct PairInfo {            // 16 bytes, built on the device once per launch
+    long long src;           // float offset of the pair's first sample in wavp
+    int out_frame;           // global frame index of frame A
+    int has_b;               // frame B exists
+};
 
 struct StftParams {
     const float *wavp;
-    const int64_t *seg_off;      // [n]
-    const int *tile_off;         // [n+1]
-    const int64_t *frame_off;    // [n+1]
-    int n_utts, n_tiles;
+    const PairInfo *pairs;
+    int n_pairs;
     float *out;
     const float *window;
     const float2 *tw;
-    const int2 *ent;
-    const int2 *seg;
-    int n_ent, n_seg;
+    const float4 *mel_w;     // [n_groups][32]
+    const int *mel_k;        // [n_groups][32] first bin of the group (multiple of 4)
+    const int *mel_band;     // [kMelSlots][32] band handled by (slot, lane), -1 = none
+    int slot_end[kMelSlots]; // cumulative group counts
+    int n_groups;
     float min_level, c1, c0;
-};
-
-struct TileInfo {
-    long long out_frame;     // global frame index of the tile's first frame
-    int n_valid;             // frames of this tile that exist
-    int pad;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -97,153 +104,191 @@ __device__ __forceinline__ float fast_log2(float x)
     return r;
 }
 
+// pair table: thread per pair
+__global__ void stft_pairs_kernel(const int64_t *__restrict__ seg_off, const int *__restrict__ pair_off,
+                                  const int64_t *__restrict__ frame_off, int n, int n_pairs,
+                                  PairInfo *__restrict__ pairs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int u = find_segment(pair_off, n, i);
+    const int k = i - pair_off[u];
+    const int n_frames = static_cast<int>(frame_off[u + 1] - frame_off[u]);
+    PairInfo pi;
+    pi.src = seg_off[u] + static_cast<long long>(k) * 2 * kHop;
+    pi.out_frame = static_cast<int>(frame_off[u]) + 2 * k;
+    pi.has_b = (2 * k + 1 < n_frames) ? 1 : 0;
+    pairs[i] = pi;
+}
+
+struct __align__(16) WarpSmem {
+    float stage[kPairFloats];            // 5120 B, TMA destination
+    float2 trans[kWarpTrans];            // 8448 B; later re-used as the interleaved magnitudes
+    float outs[2 * kMels];               // 640 B
+    uint64_t bar;
+    uint64_t pad;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(kStftThreads, 2) stft_mel_kernel(const StftParams p)
+__global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *s_stage = reinterpret_cast<float *>(smem_raw);                       // [2][kStageFloats]
-    float2 *s_trans = reinterpret_cast<float2 *>(s_stage + 2 * kStageFloats);   // [4][kWarpTrans]
-    float2 *s_tw = s_trans + 4 * kWarpTrans;                                    // [1024]
-    float *s_win = reinterpret_cast<float *>(s_tw + 1024);                      // [1024]
-    int2 *s_ent = reinterpret_cast<int2 *>(s_win + 1024);                       // [n_ent][32]
-    int2 *s_seg = s_ent + kMaxEnt * 32;                                         // [n_seg][32]
-    float *s_out = reinterpret_cast<float *>(s_seg + kMaxSeg * 32);             // [4][160]
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_out + 4 * 160);            // [2]
-    TileInfo *s_info = reinterpret_cast<TileInfo *>(s_bar + 2);                 // [2]
+    WarpSmem *ws_all = reinterpret_cast<WarpSmem *>(smem_raw);
+    float2 *s_tw = reinterpret_cast<float2 *>(ws_all + kStftWarps);        // [1024]
+    float *s_win = reinterpret_cast<float *>(s_tw + 1024);                 // [1024]
+    float4 *s_mw = reinterpret_cast<float4 *>(s_win + 1024);               // [kMaxGroups][32]
+    int *s_mk = reinterpret_cast<int *>(s_mw + kMaxGroups * 32);           // [kMaxGroups][32]
+    int *s_mb = s_mk + kMaxGroups * 32;                                    // [kMelSlots][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpSmem &ws = ws_all[warp];
 
     for (int i = tid; i < 1024; i += kStftThreads) {
         s_tw[i] = p.tw[i];
         s_win[i] = p.window[i];
     }
     if (MODE == 0) {
-        for (int i = tid; i < p.n_ent * 32; i += kStftThreads) s_ent[i] = p.ent[i];
-        for (int i = tid; i < p.n_seg * 32; i += kStftThreads) s_seg[i] = p.seg[i];
+        for (int i = tid; i < p.n_groups * 32; i += kStftThreads) {
+            s_mw[i] = p.mel_w[i];
+            s_mk[i] = p.mel_k[i];
+        }
+        for (int i = tid; i < kMelSlots * 32; i += kStftThreads) s_mb[i] = p.mel_band[i];
     }
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+    if (lane == 0) {
+        mbar_init(&ws.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();   // the only block-level barrier: tables and barriers are ready
 
-    auto issue = [&](int tile, int buf) {   // thread 0 only
-        const int u = find_segment(p.tile_off, p.n_utts, tile);
-        const int f0 = (tile - p.tile_off[u]) * kTileFrames;
-        const int n_frames = static_cast<int>(p.frame_off[u + 1] - p.frame_off[u]);
-        TileInfo ti;
-        ti.out_frame = p.frame_off[u] + f0;
-        ti.n_valid = min(kTileFrames, n_frames - f0);
-        ti.pad = 0;
-        s_info[buf] = ti;
-        mbar_expect_tx(&s_bar[buf], kStageFloats * 4);
-        tma_load_1d(s_stage + buf * kStageFloats, p.wavp + p.seg_off[u] + static_cast<int64_t>(f0) * kHop,
-                    kStageFloats * 4, &s_bar[buf]);
-    };
-
-    if (tid == 0 && static_cast<int>(blockIdx.x) < p.n_tiles) issue(blockIdx.x, 0);
-
-    float2 *trans = s_trans + warp * kWarpTrans;
-    float *mA = reinterpret_cast<float *>(trans);      // [520] aliases the transpose buffer
-    float *mB = mA + 520;
-    float *outs = s_out + warp * 160;
-
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (tid == 0) {
-            const int nt = tile + gridDim.x;
-            if (nt < p.n_tiles) issue(nt, buf ^ 1);
+    const int stride = gridDim.x * kStftWarps;
+    int pair = blockIdx.x * kStftWarps + warp;
+    PairInfo cur;
+    cur.src = 0; cur.out_frame = 0; cur.has_b = 0;
+    if (pair < p.n_pairs) {
+        cur = p.pairs[pair];
+        if (lane == 0) {
+            mbar_expect_tx(&ws.bar, kPairFloats * 4);
+            tma_load_1d(ws.stage, p.wavp + cur.src, kPairFloats * 4, &ws.bar);
         }
-        mbar_wait(&s_bar[buf], (it >> 1) & 1);
-        const TileInfo ti = s_info[buf];
-        const int fa = 2 * warp;
-        if (fa < ti.n_valid) {
-            const float *xa = s_stage + buf * kStageFloats + fa * kHop;
-            const bool has_b = (fa + 1) < ti.n_valid;
-            // a missing second frame must be exactly zero: it shares the transform with frame A
-            const float wb = has_b ? 1.0f : 0.0f;
-            float2 v[32];
+    }
+    float2 *trans = ws.trans;
+    float2 *mag2 = ws.trans;               // [520] (|A[k]|, |B[k]|) without the common factor 1/2
+    uint32_t parity = 0;
+
+    for (; pair < p.n_pairs; pair += stride) {
+        // prefetch the descriptor of this warp's next pair (all lanes, same address)
+        const int next = pair + stride;
+        PairInfo nxt = cur;
+        if (next < p.n_pairs) nxt = p.pairs[next];
+
+        mbar_wait(&ws.bar, parity);
+        parity ^= 1;
+        float2 v[32];
+        if (cur.has_b) {
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
                 const int n = lane + 32 * m;
-                const float w = s_win[n];
-                const float xb = has_b ? xa[n + kHop] : 0.0f;
-                v[m] = make_float2(xa[n] * w, xb * (w * wb));
+                v[m] = cscale(make_float2(ws.stage[n], ws.stage[n + kHop]), s_win[n]);
             }
-            fft32_dif(v);
+        } else {   // the missing second frame must be exactly zero: it shares the transform with A
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const int k1 = bitrev5(r);
-                float2 y = v[r];
-                if (k1 != 0) {
-                    const float2 t = s_tw[k1 * 32 + lane];
-                    y = make_float2(v[r].x * t.x - v[r].y * t.y, v[r].x * t.y + v[r].y * t.x);
-                }
-                trans[lane * kTransStride + k1] = y;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = trans[j * kTransStride + lane];
-            __syncwarp();
-            fft32_dif(v);
-
-            // separate the two real spectra and take magnitudes (without the common factor 1/2)
-            const int partner = (32 - lane) & 31;
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) {
-                const float2 mine = v[bitrev5(k2)];
-                const float2 prov = v[bitrev5(31 - k2)];
-                float2 got;
-                got.x = __shfl_sync(0xffffffffu, prov.x, partner);
-                got.y = __shfl_sync(0xffffffffu, prov.y, partner);
-                if (lane == 0) got = v[bitrev5((32 - k2) & 31)];
-                const float ar = mine.x + got.x, ai = mine.y - got.y;
-                const float br = mine.x - got.x, bi = mine.y + got.y;
-                mA[lane + 32 * k2] = fast_sqrt(ar * ar + ai * ai);
-                mB[lane + 32 * k2] = fast_sqrt(br * br + bi * bi);
-            }
-            if (lane == 0) {   // k = 512 pairs with itself
-                const float2 x = v[bitrev5(16)];
-                mA[512] = 2.0f * fabsf(x.x);
-                mB[512] = 2.0f * fabsf(x.y);
-            }
-            __syncwarp();
-
-            if (MODE == 0) {
-                int e = 0;
-                for (int s = 0; s < p.n_seg; ++s) {
-                    const int2 sg = s_seg[s * 32 + lane];
-                    float accA = 0.0f, accB = 0.0f;
-                    for (; e < sg.x; ++e) {
-                        const int2 en = s_ent[e * 32 + lane];
-                        const float w = __int_as_float(en.y);
-                        accA = fmaf(w, mA[en.x], accA);
-                        accB = fmaf(w, mB[en.x], accB);
-                    }
-                    if (sg.y >= 0) {
-                        outs[sg.y] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, accA)), p.c0);
-                        outs[kMels + sg.y] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, accB)), p.c0);
-                    }
-                }
-                __syncwarp();
-                float *dst = p.out + (ti.out_frame + fa) * kMels;
-                const int n_out = has_b ? 2 * kMels : kMels;
-                for (int i = lane; i < n_out; i += 32) dst[i] = outs[i];
-            } else {
-                float *dst = p.out + (ti.out_frame + fa) * kBins;
-                for (int i = lane; i < kBins; i += 32) dst[i] = 0.5f * mA[i];
-                if (has_b)
-                    for (int i = lane; i < kBins; i += 32) dst[kBins + i] = 0.5f * mB[i];
+            for (int m = 0; m < 32; ++m) {
+                const int n = lane + 32 * m;
+                v[m] = make_float2(ws.stage[n] * s_win[n], 0.0f);
             }
         }
-        __syncthreads();   // stage[buf] and the per-warp buffers are free again
+        __syncwarp();                      // every lane has consumed the stage buffer
+        if (lane == 0 && next < p.n_pairs) {
+            mbar_expect_tx(&ws.bar, kPairFloats * 4);
+            tma_load_1d(ws.stage, p.wavp + nxt.src, kPairFloats * 4, &ws.bar);
+        }
+
+        fft32_dif(v);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int k1 = bitrev5(r);
+            float2 y = v[r];
+            if (k1 != 0) {
+                const float2 t = s_tw[k1 * 32 + lane];
+                y = make_float2(v[r].x * t.x - v[r].y * t.y, v[r].x * t.y + v[r].y * t.x);
+            }
+            trans[lane * kTransStride + k1] = y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = trans[j * kTransStride + lane];
+        __syncwarp();
+        fft32_dif(v);
+
+        // separate the two real spectra: with X = v, P = X[1024-k] from the partner lane,
+        //   2A = X + conj(P) = (Xr+Pr, Xi-Pi),   2iB = X - conj(P) = (Xr-Pr, Xi+Pi)
+        // Magnitudes are stored as (|A[k]|, |B[k]|) pairs.  A 4-bin group is 32 bytes = two 16-byte
+        // halves; a plain layout would put every first half in an even 16-byte bank group and every
+        // second half in an odd one, so a 128-bit load could only ever use half the banks.  Swapping
+        // the halves of groups 4..7 (mod 8) spreads the same half of 8 consecutive groups over all 8
+        // bank groups: element k lives at k ^ 2 when bit 4 of k is set (for k = lane + 32 k2 that is
+        // lane >= 16).  The mel tables hold the swizzled address of the first half; the second half is
+        // at that address ^ 2.
+        const int partner = (32 - lane) & 31;
+        const int swz = (lane & 16) >> 3;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const float2 mine = v[bitrev5(k2)];
+            const float2 prov = v[bitrev5(31 - k2)];
+            float2 got;
+            got.x = __shfl_sync(0xffffffffu, prov.x, partner);
+            got.y = __shfl_sync(0xffffffffu, prov.y, partner);
+            if (lane == 0) got = v[bitrev5((32 - k2) & 31)];
+            const float2 s = cadd(mine, got);      // (ar, bi)
+            const float2 d = csub(mine, got);      // (br, ai)
+            const float2 s2 = cmul2(s, s);         // (ar^2, bi^2)
+            mag2[(lane + 32 * k2) ^ swz] = make_float2(fast_sqrt(fmaf(d.y, d.y, s2.x)), fast_sqrt(fmaf(d.x, d.x, s2.y)));
+        }
+        if (lane == 0) {   // k = 512 pairs with itself
+            const float2 x = v[bitrev5(16)];
+            mag2[512] = make_float2(2.0f * fabsf(x.x), 2.0f * fabsf(x.y));
+        }
+        __syncwarp();
+
+        if (MODE == 0) {
+            int g = 0;
+#pragma unroll
+            for (int s = 0; s < kMelSlots; ++s) {
+                float2 acc = make_float2(0.0f, 0.0f);
+                const int gend = p.slot_end[s];
+                for (; g < gend; ++g) {
+                    const int k0 = s_mk[g * 32 + lane];
+                    const float4 w = s_mw[g * 32 + lane];
+                    const float4 m01 = *reinterpret_cast<const float4 *>(mag2 + k0);          // swizzled first half
+                    const float4 m23 = *reinterpret_cast<const float4 *>(mag2 + (k0 ^ 2));
+                    acc = cfma_s(make_float2(m01.x, m01.y), w.x, acc);
+                    acc = cfma_s(make_float2(m01.z, m01.w), w.y, acc);
+                    acc = cfma_s(make_float2(m23.x, m23.y), w.z, acc);
+                    acc = cfma_s(make_float2(m23.z, m23.w), w.w, acc);
+                }
+                const int band = s_mb[s * 32 + lane];
+                if (band >= 0) {
+                    ws.outs[band] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, acc.x)), p.c0);
+                    ws.outs[kMels + band] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, acc.y)), p.c0);
+                }
+            }
+            __syncwarp();
+            float *dst = p.out + static_cast<long long>(cur.out_frame) * kMels;
+            const int n_out = cur.has_b ? 2 * kMels : kMels;
+            for (int i = lane; i < n_out; i += 32) dst[i] = ws.outs[i];
+        } else {
+            float *dst = p.out + static_cast<long long>(cur.out_frame) * kBins;
+            for (int i = lane; i < kBins; i += 32) dst[i] = 0.5f * mag2[i ^ ((i & 16) >> 3)].x;
+            if (cur.has_b)
+                for (int i = lane; i < kBins; i += 32) dst[kBins + i] = 0.5f * mag2[i ^ ((i & 16) >> 3)].y;
+        }
+        __syncwarp();                      // mag2 / outs are free again
+        cur = nxt;
     }
 }
 
-constexpr size_t kStftSmem = 2 * kStageFloats * 4 + 4 * kWarpTrans * 8 + 1024 * 8 + 1024 * 4 +
-                             kMaxEnt * 32 * 8 + kMaxSeg * 32 * 8 + 4 * 160 * 4 + 2 * 8 + 2 * 16;
+constexpr size_t kStftSmem = kStftWarps * sizeof(WarpSmem) + 1024 * 8 + 1024 * 4 + kMaxGroups * 32 * (16 + 4) +
+                             kMelSlots * 32 * 4;
 
 // ---- reflect padding into the segment layout (np.pad(x, 512, 'reflect'), utils.py:20) ---------
 __global__ void pad_reflect_kernel(const float *__restrict__ wav, const int64_t *__restrict__ off,
@@ -298,39 +343,47 @@ int pad_reflect(ssfe_ctx *ctx, const float *wav_dev, const int64_t *offsets_host
 int stft_padded(ssfe_ctx *ctx, const float *wavp, const int64_t *seg_off_host, const int64_t *frames_host,
                 int n, int mode, float *out)
 {
-    std::vector<int> tile_off(n + 1);
+    std::vector<int> pair_off(n + 1);
     std::vector<int64_t> frame_off(n + 1);
-    int64_t tiles = 0, frames = 0;
+    int64_t pairs = 0, frames = 0;
     for (int i = 0; i < n; ++i) {
-        tile_off[i] = static_cast<int>(tiles);
+        pair_off[i] = static_cast<int>(pairs);
         frame_off[i] = frames;
-        tiles += (frames_host[i] + kTileFrames - 1) / kTileFrames;
+        pairs += (frames_host[i] + 1) / 2;
         frames += frames_host[i];
-        if (tiles > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (tiles)");
+        if (frames > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (frames)");
     }
-    tile_off[n] = static_cast<int>(tiles);
+    pair_off[n] = static_cast<int>(pairs);
     frame_off[n] = frames;
-    if (tiles == 0) return SSFE_OK;
+    if (pairs == 0) return SSFE_OK;
+    int rc = ensure(ctx, ctx->ws.tiles, pairs * sizeof(PairInfo));
+    if (rc) return rc;
+
+    const int64_t *d_seg = upload(ctx, seg_off_host, n);
+    const int *d_pair_off = upload(ctx, pair_off.data(), n + 1);
+    const int64_t *d_frame_off = upload(ctx, frame_off.data(), n + 1);
+    if (!d_seg || !d_pair_off || !d_frame_off) return SSFE_ERR_NOMEM;
+    PairInfo *d_pairs = static_cast<PairInfo *>(ctx->ws.tiles.p);
+    stft_pairs_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, ctx->stream>>>(
+        d_seg, d_pair_off, d_frame_off, n, static_cast<int>(pairs), d_pairs);
+    SSFE_LAUNCHED(ctx);
 
     StftParams p;
     p.wavp = wavp;
-    p.seg_off = upload(ctx, seg_off_host, n);
-    p.tile_off = upload(ctx, tile_off.data(), n + 1);
-    p.frame_off = upload(ctx, frame_off.data(), n + 1);
-    if (!p.seg_off || !p.tile_off || !p.frame_off) return SSFE_ERR_NOMEM;
-    p.n_utts = n;
-    p.n_tiles = static_cast<int>(tiles);
+    p.pairs = d_pairs;
+    p.n_pairs = static_cast<int>(pairs);
     p.out = out;
     p.window = ctx->d_window;
     p.tw = ctx->d_tw;
-    p.ent = ctx->mel.ent;
-    p.seg = ctx->mel.seg;
-    p.n_ent = ctx->mel.n_entries;
-    p.n_seg = ctx->mel.n_seg;
+    p.mel_w = ctx->mel.w4;
+    p.mel_k = ctx->mel.k0;
+    p.mel_band = ctx->mel.band;
+    for (int s = 0; s < kMelSlots; ++s) p.slot_end[s] = ctx->mel.slot_end[s];
+    p.n_groups = ctx->mel.n_groups;
     p.min_level = static_cast<float>(ctx->cfg.min_level);
     p.c1 = static_cast<float>(0.2 * std::log10(2.0));
     p.c0 = static_cast<float>((100.0 - ctx->cfg.ref_db) / 100.0);
-    const int grid = static_cast<int>(std::min<int64_t>(tiles, 2LL * ctx->num_sms));
+    const int grid = static_cast<int>(std::min<int64_t>((pairs + kStftWarps - 1) / kStftWarps, ctx->num_sms));
     if (mode == 0)
         stft_mel_kernel<0><<<grid, kStftThreads, kStftSmem, ctx->stream>>>(p);
     else
@@ -356,57 +409,79 @@ int init_stft_tables(ssfe_ctx *ctx)
     SSFE_CUDA(ctx, cudaMemcpy(ctx->d_window, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpy(ctx->d_tw, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
 
-    // sparse mel: bands -> lanes by longest-processing-time-first on the non-zero count
+    // mel: every band is a run of bins [kb, ke]; it is covered by aligned groups of 4 bins.  Bands are
+    // sorted by group count and dealt to (slot, lane): slot s of lane l handles band order[32 s + l], so
+    // the group loop of a slot has the same trip count for the whole warp (short bands get zero groups).
     const float *mb = ctx->mel_basis.data();   // [bin][band]
-    std::vector<std::vector<int>> bins(kMels);
-    for (int k = 0; k < kBins; ++k)
-        for (int m = 0; m < kMels; ++m)
-            if (mb[k * kMels + m] != 0.0f) bins[m].push_back(k);
+    int kb[kMels], ke[kMels], ng[kMels];
+    for (int m = 0; m < kMels; ++m) {
+        kb[m] = -1;
+        ke[m] = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (mb[k * kMels + m] != 0.0f) {
+                if (kb[m] < 0) kb[m] = k;
+                ke[m] = k;
+            }
+        ng[m] = (kb[m] < 0) ? 0 : ((ke[m] | 3) + 1 - (kb[m] & ~3)) / 4;
+    }
     std::vector<int> order(kMels);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int a, int b) { return bins[a].size() > bins[b].size(); });
-    std::vector<std::vector<int>> lane_bands(32);
-    std::vector<size_t> load(32, 0);
-    for (int m : order) {
-        int best = 0;
-        for (int l = 1; l < 32; ++l)
-            if (load[l] < load[best]) best = l;
-        lane_bands[best].push_back(m);
-        load[best] += bins[m].size();
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ng[a] > ng[b]; });
+    static_assert(kMelSlots * 32 >= kMels, "not enough (slot, lane) cells for the bands");
+    int slot_groups[kMelSlots], total = 0;
+    for (int s = 0; s < kMelSlots; ++s) {
+        slot_groups[s] = 0;
+        for (int l = 0; l < 32 && s * 32 + l < kMels; ++l) slot_groups[s] = std::max(slot_groups[s], ng[order[s * 32 + l]]);
+        total += slot_groups[s];
+        ctx->mel.slot_end[s] = total;
     }
-    size_t E = 0, S = 0;
-    for (int l = 0; l < 32; ++l) {
-        E = std::max(E, load[l]);
-        S = std::max(S, lane_bands[l].size());
-    }
-    if (E > kMaxEnt || S > kMaxSeg || E == 0)
-        return set_error(ctx, SSFE_ERR_INVALID, "mel basis too dense for the fused kernel (%zu entries/lane, %zu bands/lane)", E, S);
-    std::vector<int2> ent(E * 32, make_int2(0, 0)), seg(S * 32, make_int2(0, -1));
-    for (int l = 0; l < 32; ++l) {
-        int e = 0;
-        for (size_t s = 0; s < S; ++s) {
-            if (s < lane_bands[l].size()) {
-                const int m = lane_bands[l][s];
-                for (int k : bins[m]) {
-                    const float w = 0.5f * mb[k * kMels + m];   // exact: folds the 1/2 of the frame split
-                    int wi;
-                    std::memcpy(&wi, &w, 4);
-                    ent[e * 32 + l] = make_int2(k, wi);
-                    ++e;
-                }
-                seg[s * 32 + l] = make_int2(e, m);
-            } else {
-                seg[s * 32 + l] = make_int2(e, -1);
+    if (total > kMaxGroups || total == 0)
+        return set_error(ctx, SSFE_ERR_INVALID, "mel basis too dense for the fused kernel (%d groups per lane)", total);
+    std::vector<float4> w4(static_cast<size_t>(total) * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> k0(static_cast<size_t>(total) * 32, 0), band(kMelSlots * 32, -1);
+    int gbase = 0;
+    for (int s = 0; s < kMelSlots; ++s) {
+        // place the slot's bands on lanes so that the 8 lanes of a quarter warp (one 128-bit shared
+        // memory wavefront) start in different 16-byte bank groups: first group index distinct mod 8
+        int lane_band[32];
+        bool used[4][8] = {};
+        int fill[4] = {0, 0, 0, 0};
+        for (int l = 0; l < 32; ++l) lane_band[l] = -1;
+        std::vector<int> leftover;
+        for (int l = 0; l < 32 && s * 32 + l < kMels; ++l) {
+            const int m = order[s * 32 + l];
+            const int res = (kb[m] >> 2) & 7;
+            int q = -1;
+            for (int c = 0; c < 4; ++c)
+                if (!used[c][res] && fill[c] < 8 && (q < 0 || fill[c] < fill[q])) q = c;
+            if (q < 0) { leftover.push_back(m); continue; }
+            used[q][res] = true;
+            lane_band[q * 8 + fill[q]++] = m;
+        }
+        for (int m : leftover)
+            for (int l = 0; l < 32; ++l)
+                if (lane_band[l] < 0) { lane_band[l] = m; break; }
+        for (int l = 0; l < 32; ++l) {
+            const int m = lane_band[l];
+            if (m < 0) continue;
+            band[s * 32 + l] = m;
+            for (int g = 0; g < ng[m]; ++g) {
+                const int k = (kb[m] & ~3) + 4 * g;
+                float wv[4];
+                for (int q = 0; q < 4; ++q) wv[q] = (k + q < kBins) ? 0.5f * mb[(k + q) * kMels + m] : 0.0f;   // 1/2 of the frame split, exact
+                w4[(gbase + g) * 32 + l] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+                k0[(gbase + g) * 32 + l] = k ^ ((k & 16) >> 3);      // swizzled address of the first half
             }
         }
+        gbase += slot_groups[s];
     }
-    ctx->mel.n_entries = static_cast<int>(E);
-    ctx->mel.n_seg = static_cast<int>(S);
-    SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.ent, ent.size() * sizeof(int2)));
-    SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.seg, seg.size() * sizeof(int2)));
-    SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.ent, ent.data(), ent.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.seg, seg.data(), seg.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    ctx->mel.n_groups = total;
+    SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.w4, w4.size() * sizeof(float4)));
+    SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.k0, k0.size() * sizeof(int)));
+    SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.band, band.size() * sizeof(int)));
+    SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.w4, w4.data(), w4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.k0, k0.data(), k0.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaFuncSetAttribute(stft_mel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kStftSmem)));
     SSFE_CUDA(ctx, cudaFuncSetAttribute(stft_mel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -418,12 +493,14 @@ void free_stft_tables(ssfe_ctx *ctx)
 {
     cudaFree(ctx->d_window);
     cudaFree(ctx->d_tw);
-    cudaFree(ctx->mel.ent);
-    cudaFree(ctx->mel.seg);
+    cudaFree(ctx->mel.w4);
+    cudaFree(ctx->mel.k0);
+    cudaFree(ctx->mel.band);
     ctx->d_window = nullptr;
     ctx->d_tw = nullptr;
-    ctx->mel.ent = nullptr;
-    ctx->mel.seg = nullptr;
+    ctx->mel.w4 = nullptr;
+    ctx->mel.k0 = nullptr;
+    ctx->mel.band = nullptr;
 }
 
 }  // namespace ssfe

@@ -140,6 +140,28 @@ def test_extract_host_matches_device_path(fe, golden_dir):
     assert np.array_equal(h["bins"], res["bins"].cpu().numpy())
 
 
+def test_extract_host_many_sub_batches(golden_dir, monkeypatch):
+    """The pipelined host path (up-front dither, double-buffered H2D / kernels / D2H) with the
+    sub-batch size forced down so that every utterance is its own sub-batch."""
+    from speechsplit_b200 import FrontEnd
+    monkeypatch.setenv("SSFE_HOST_CHUNK_SAMPLES", "1000")
+    f2 = FrontEnd(0)
+    try:
+        pcm, meta = _golden_batch(golden_dir, NAMES)
+        ref = _extract(f2, pcm, meta, ("mel", "f0_norm", "bins"))
+        off = np.concatenate([[0], np.cumsum([len(p) for p in pcm])]).astype(np.int64)
+        lo = [50.0 if m["gender"] == "M" else 100.0 for m in meta]
+        hi = [250.0 if m["gender"] == "M" else 600.0 for m in meta]
+        for _ in range(2):      # twice: slot reuse and the dither-buffer hand-over between calls
+            h = f2.extract_host(np.concatenate(pcm), off, lo, hi, [int(m["spk"][1:]) for m in meta],
+                                [m["skip"] for m in meta])
+            assert np.array_equal(h["mel"], ref["mel"].cpu().numpy())
+            assert np.array_equal(h["f0_norm"], ref["f0_norm"].cpu().numpy(), equal_nan=True)
+            assert np.array_equal(h["bins"], ref["bins"].cpu().numpy())
+    finally:
+        f2.close()
+
+
 def test_extract_vs_oracle_small_corpus(fe):
     """A fresh synthetic mini-corpus (6 speakers x 4 files) against the oracle pipeline."""
     metas = make_manifest(6, 4, seed=17)
