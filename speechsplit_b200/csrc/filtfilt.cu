@@ -319,14 +319,14 @@ __device__ __forceinline__ dd dd_two_sum(double a, double b)
     const double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
     return {s, e};
 }
+// "sloppy" double-double sum (Dekker): error ~ 2^-104 relative to |a|+|b|, half the dependent depth of
+// the IEEE-style version; the carry only needs ~2^-80
 __device__ __forceinline__ dd dd_add(dd a, dd b)
 {
-    dd s = dd_two_sum(a.hi, b.hi);
-    const dd t = dd_two_sum(a.lo, b.lo);
-    s.lo = __dadd_rn(s.lo, t.hi);
-    s = dd_two_sum(s.hi, s.lo);           // (fast two-sum would do; keep the safe form)
-    s.lo = __dadd_rn(s.lo, t.lo);
-    return dd_two_sum(s.hi, s.lo);
+    const dd s = dd_two_sum(a.hi, b.hi);
+    const double e = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
+    const double hi = __dadd_rn(s.hi, e);
+    return {hi, __dsub_rn(e, __dsub_rn(hi, s.hi))};
 }
 __device__ __forceinline__ dd dd_mul(dd a, dd b)
 {
@@ -334,7 +334,8 @@ __device__ __forceinline__ dd dd_mul(dd a, dd b)
     double e = __fma_rn(a.hi, b.hi, -p);
     e = __fma_rn(a.hi, b.lo, e);
     e = __fma_rn(a.lo, b.hi, e);
-    return dd_two_sum(p, e);
+    const double hi = __dadd_rn(p, e);
+    return {hi, __dsub_rn(e, __dsub_rn(hi, p))};
 }
 
 // one thread per utterance: turn the zero-state finals into true chunk-entry states
@@ -367,13 +368,17 @@ __global__ void filt_carry_kernel(const FiltParams p)
         dd zn[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            dd acc = {sc[i], 0.0};
+            // the kernel is a latency chain (one utterance per thread): sum the five products as a
+            // tree, not a chain
+            dd pr[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const dd m = {c_filt.m_hi[i * 5 + k], c_filt.m_lo[i * 5 + k]};
-                acc = dd_add(acc, dd_mul(m, z[k]));
+                pr[k] = dd_mul(m, z[k]);
             }
-            zn[i] = acc;
+            const dd s01 = dd_add(pr[0], pr[1]), s23 = dd_add(pr[2], pr[3]);
+            const dd s4c = dd_add(pr[4], dd{sc[i], 0.0});
+            zn[i] = dd_add(dd_add(s01, s23), s4c);
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) z[i] = zn[i];

@@ -91,21 +91,26 @@ __global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__re
                 r_out = rq[r0].out_off;
             }
         }
-        if (r0 < job.n_req && r_beg < d0 + 312 && tid < 312) {
-            const uint64_t d = d0 + tid;
-            uint64_t b = r_beg, e = r_end;
-            int64_t oo = r_out;
-            int r = r0;
-            while (r < job.n_req && e <= d) {              // rare: the block spans a request boundary
-                ++r;
-                if (r < job.n_req) {
-                    b = rq[r].skip;
-                    e = b + static_cast<uint64_t>(rq[r].count);
-                    oo = rq[r].out_off;
+        if (r0 < job.n_req && tid < 312) {
+            if (r_beg <= d0 && d0 + 312 <= r_end) {
+                // common case: the whole block belongs to the current request
+                out[r_out + static_cast<int64_t>(d0 - r_beg) + tid] = *reinterpret_cast<const uint2 *>(nw + 2 * tid);
+            } else if (r_beg < d0 + 312) {
+                const uint64_t d = d0 + tid;
+                uint64_t b = r_beg, e = r_end;
+                int64_t oo = r_out;
+                int r = r0;
+                while (r < job.n_req && e <= d) {          // the block spans a request boundary
+                    ++r;
+                    if (r < job.n_req) {
+                        b = rq[r].skip;
+                        e = b + static_cast<uint64_t>(rq[r].count);
+                        oo = rq[r].out_off;
+                    }
                 }
+                if (r < job.n_req && d >= b)     // raw word pair; tempering + conversion happen in the consumer
+                    out[oo + static_cast<int64_t>(d - b)] = *reinterpret_cast<const uint2 *>(nw + 2 * tid);
             }
-            if (r < job.n_req && d >= b)     // raw word pair; tempering + conversion happen in the consumer
-                out[oo + static_cast<int64_t>(d - b)] = *reinterpret_cast<const uint2 *>(nw + 2 * tid);
         }
         // no second barrier: the next twist writes the buffer whose last readers passed the barrier
         // above, and only reads the buffer this output phase reads.

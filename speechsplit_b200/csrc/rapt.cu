@@ -47,6 +47,7 @@ struct RaptConsts {
     RaptCfg cfg[2];
     float co[kNco];
     float cand_thresh, tcost, tfact_a, tfact_s, vbias, ffact, preemp;
+    float ln2, fdouble, freqwt;
     int size_frame_hist, size_frame_out;
 };
 
@@ -57,6 +58,8 @@ struct RaptUtt {
 
 struct RaptTables {
     float *d_ferr = nullptr;       // voiced->voiced transition cost [cfg][lag1][lag2]
+    double *d_log = nullptr;       // log(lag), lag < kMaxLag
+    int use_log = 0;
     float *d_w479 = nullptr, *d_w480 = nullptr;
     RaptConsts host;
     // where the last rapt_run left its per-frame records (ssfe_rapt_dump)
@@ -83,6 +86,8 @@ struct RaptParams {
     float *f0c;                    // [fr][20] F0 (Hz) the candidate would emit, 0 = unvoiced
     float *sta, *rr;
     const float *ferr;
+    const double *log_lag;         // [kMaxLag] log(lag) in double
+    int use_log;                   // the log-difference shortcut reproduces the table for every pair
     const float *w479, *w480;
     float *out;                    // log-F0
 };
@@ -556,36 +561,77 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
 constexpr size_t kStatSmem = (kStatSpan + kStatSpan / 256 + 2 + 2 * kStatW + kStatFrames * 20) * sizeof(float);
 
 // ---- K4 ------------------------------------------------------------------------------------
+// The kernel is one latency chain per utterance, so every round trip to global memory inside the
+// frame loop is removed: the records of frame g+1 are fetched while frame g is processed, and the
+// voiced->voiced jump cost  float(log(lag2 / lag1))  is formed from a 321-entry table of log(lag)
+// held in shared memory (one value per candidate, the previous frame's arrive by shuffle) instead of
+// being gathered from the 257 x 257 table in L2.  log(l2) - log(l1) rounded to float is verified on the
+// host, for every lag pair, to equal the original's float(log(l2 / l1)); if it ever does not, the
+// kernel falls back to the exact table (use_log == 0).
 constexpr int kDpWarps = 4;
+constexpr int kMaxLag = 336;
+
+__device__ __forceinline__ float jump_cost(float ftemp, float ln2, float fdouble, float freqwt)
+{
+    // the original's precision mix: fabs() is the double function
+    float ttemp = static_cast<float>(fabs(static_cast<double>(ftemp)));
+    float ft1 = static_cast<float>(static_cast<double>(fdouble) + fabs(static_cast<double>(ftemp + ln2)));
+    if (ttemp > ft1) ttemp = ft1;
+    ft1 = static_cast<float>(static_cast<double>(fdouble) + fabs(static_cast<double>(ftemp - ln2)));
+    if (ttemp > ft1) ttemp = ft1;
+    return ttemp * freqwt;
+}
 
 __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams p)
 {
     __shared__ unsigned char s_ring[kDpWarps][kRing][kCMax];
+    __shared__ unsigned char s_path[kDpWarps][kRing];
+    __shared__ double s_log[kMaxLag];
+    for (int i = threadIdx.x; i < kMaxLag; i += blockDim.x) s_log[i] = p.log_lag[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int u = blockIdx.x * kDpWarps + w;
     if (u >= p.n) return;
     const RaptUtt ut = p.utts[u];
     const RaptCfg &cf = c_rapt.cfg[ut.cfg];
     const float *ferr_tab = p.ferr + cf.table_off;
+    const bool use_log = p.use_log != 0;
     float *out = p.out + ut.out_off;
     unsigned char(*ring)[kCMax] = s_ring[w];
+    unsigned char *path = s_path[w];
     const unsigned full_mask = 0xffffffffu;
 
     float d_prev = 0.0f;
     int loc_prev = -1, ncandp = 0;
+    double lg_prev = 0.0;
     int head = -1, tail = 0, num_active = 0;
     int my_pre = 0;
+    // software pipeline: records of the next frame
+    int n_nc = 0, n_loc = -1;
+    float n_mp = 0.0f, n_sta = 0.0f, n_rr = 1.0f;
+    auto fetch = [&](int g) {
+        if (g < ut.n_fr) {
+            const long long gf = ut.fr_off + g;
+            n_nc = p.ncand[gf];
+            n_loc = (lane < kCMax) ? p.loc[gf * kCMax + lane] : -1;
+            n_mp = (lane < kCMax) ? p.mp[gf * kCMax + lane] : 0.0f;
+            n_sta = p.sta[gf];
+            n_rr = p.rr[gf];
+        }
+    };
+    fetch(0);
     for (int r = 0; r <= ut.R_last; ++r) {
         const int nfr = (r < ut.R_last) ? cf.F : ut.nl;
         const bool last_time = (r == ut.R_last);
         num_active += nfr;
         for (int i = 0; i < nfr; ++i) {
             const int g = r * cf.F + i;
-            const long long gf = ut.fr_off + g;
-            const int ncand = p.ncand[gf];
-            const int loc = (lane < ncand) ? p.loc[gf * kCMax + lane] : -1;
-            const float mp = (lane < ncand) ? p.mp[gf * kCMax + lane] : 0.0f;
-            const float sta = p.sta[gf], rr = p.rr[gf];
+            const int ncand = n_nc;
+            const int loc = (lane < ncand) ? n_loc : -1;
+            const float mp = (lane < ncand) ? n_mp : 0.0f;
+            const float sta = n_sta, rr = n_rr;
+            fetch(g + 1);
+            const double lg = (loc > 0) ? s_log[loc] : 0.0;
             const float v_from_uv = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a / rr);
             const float uv_from_v = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr);
             float errmin = FLT_MAX;
@@ -594,12 +640,19 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
             for (int j = 0; j < kCMax; ++j) {
                 const int loc1 = __shfl_sync(full_mask, loc_prev, j);
                 const float dp = __shfl_sync(full_mask, d_prev, j);
+                const double lg1 = __shfl_sync(full_mask, lg_prev, j);
                 if (j < ncandp) {
                     float ferr;
-                    if (loc > 0)
-                        ferr = (loc1 > 0) ? ferr_tab[(loc1 - cf.start) * cf.nlags + (loc - cf.start)] : v_from_uv;
-                    else
+                    if (loc > 0) {
+                        if (loc1 > 0) {
+                            if (use_log) ferr = jump_cost(static_cast<float>(lg - lg1), c_rapt.ln2, c_rapt.fdouble, c_rapt.freqwt);
+                            else ferr = ferr_tab[(loc1 - cf.start) * cf.nlags + (loc - cf.start)];
+                        } else {
+                            ferr = v_from_uv;
+                        }
+                    } else {
                         ferr = (loc1 > 0) ? uv_from_v : 0.0f;
+                    }
                     const float err = ferr + dp;
                     if (err < errmin) { errmin = err; minloc = j; }
                 }
@@ -610,6 +663,7 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
             if (lane < kCMax) ring[g & (kRing - 1)][lane] = static_cast<unsigned char>(my_pre);
             d_prev = dcur;
             loc_prev = loc;
+            lg_prev = lg;
             ncandp = ncand;
             head = g;
         }
@@ -653,13 +707,18 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
                 }
             }
             if (done) {
+                // lane 0 follows the back pointers (shared memory only), then all lanes emit
                 if (lane == 0) {
                     int bc = best_cand;
                     for (int frm = cmpth; frm >= tail; --frm) {
-                        const float f0 = p.f0c[(ut.fr_off + frm) * kCMax + bc];
-                        out[frm] = (f0 == 0.0f) ? kUnvoiced : static_cast<float>(log(static_cast<double>(f0)));
+                        path[frm & (kRing - 1)] = static_cast<unsigned char>(bc);
                         bc = ring[frm & (kRing - 1)][bc];
                     }
+                }
+                __syncwarp();
+                for (int frm = tail + lane; frm <= cmpth; frm += 32) {
+                    const float f0 = p.f0c[(ut.fr_off + frm) * kCMax + path[frm & (kRing - 1)]];
+                    out[frm] = (f0 == 0.0f) ? kUnvoiced : static_cast<float>(log(static_cast<double>(f0)));
                 }
                 num_active -= (cmpth - tail + 1);
                 tail = cmpth + 1;
@@ -700,6 +759,12 @@ int init_rapt(ssfe_ctx *ctx)
     h.size_frame_out = static_cast<int>(1.0 / frame_int);
     const float ln2 = static_cast<float>(log(2.0));
     const float freqwt = freq_weight / frame_int;
+    h.ln2 = ln2;
+    h.fdouble = double_cost;
+    h.freqwt = freqwt;
+    std::vector<double> log_lag(336, 0.0);
+    for (int l = 1; l < 336; ++l) log_lag[l] = log(static_cast<double>(l));
+    bool log_ok = true;
     const float ranges[2][2] = {{50.0f, 250.0f}, {100.0f, 600.0f}};
     std::vector<float> ferr;
     for (int c = 0; c < 2; ++c) {
@@ -736,6 +801,15 @@ int init_rapt(ssfe_ctx *ctx)
                 ft1 = double_cost + fabs(ftemp - ln2);
                 if (ttemp > ft1) ttemp = ft1;
                 ferr.push_back(ttemp * freqwt);
+                // the shortcut the DP kernel uses: log(l2) - log(l1), rounded to float
+                if (l1 >= 336 || l2 >= 336) { log_ok = false; continue; }
+                float f2 = static_cast<float>(log_lag[l2] - log_lag[l1]);
+                float t2 = fabs(f2);
+                float g1 = double_cost + fabs(f2 + ln2);
+                if (t2 > g1) t2 = g1;
+                g1 = double_cost + fabs(f2 - ln2);
+                if (t2 > g1) t2 = g1;
+                if (t2 * freqwt != ferr.back()) log_ok = false;
             }
     }
     // decimation filter: Hanning-windowed sinc, 81 taps, cut-off 0.5/8 cycles per sample
@@ -762,6 +836,9 @@ int init_rapt(ssfe_ctx *ctx)
         const double arg = 3.1415927 * 2.0 / n, half = 0.5;
         for (int i = 0; i < n; ++i) wv[i] = (half - half * cos((half + static_cast<double>(i)) * arg));
     }
+    T->use_log = log_ok ? 1 : 0;
+    SSFE_CUDA(ctx, cudaMalloc(&T->d_log, log_lag.size() * sizeof(double)));
+    SSFE_CUDA(ctx, cudaMemcpy(T->d_log, log_lag.data(), log_lag.size() * sizeof(double), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMalloc(&T->d_ferr, ferr.size() * sizeof(float)));
     SSFE_CUDA(ctx, cudaMalloc(&T->d_w479, kStatW * sizeof(float)));
     SSFE_CUDA(ctx, cudaMalloc(&T->d_w480, kStatW * sizeof(float)));
@@ -778,6 +855,7 @@ void free_rapt(ssfe_ctx *ctx)
 {
     if (!ctx->rapt) return;
     cudaFree(ctx->rapt->d_ferr);
+    cudaFree(ctx->rapt->d_log);
     cudaFree(ctx->rapt->d_w479);
     cudaFree(ctx->rapt->d_w480);
     delete ctx->rapt;
@@ -859,6 +937,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     p.loc = reinterpret_cast<short *>(p.rr + frp);
     p.ncand = reinterpret_cast<unsigned char *>(p.loc + frp * kCMax);
     p.ferr = ctx->rapt->d_ferr;
+    p.log_lag = ctx->rapt->d_log;
+    p.use_log = ctx->rapt->use_log;
     p.w479 = ctx->rapt->d_w479;
     p.w480 = ctx->rapt->d_w480;
     p.out = f0_dev;
