@@ -46,7 +46,8 @@ struct FiltParams {
     const int64_t *fix_off;       // [n+1] fixed (post-append) offsets
     const int *chunk_off;         // [n+1] prefix of chunk counts
     int n, n_chunks, chunk_len;
-    double *state;                // [n_chunks][5] zero-state finals, then overwritten by z_in
+    double *state;                // [n_chunks][5] zero-state finals of the local pass
+    double *zin;                  // [n_chunks][5] true chunk-entry states (carry -> final pass)
     // outputs of the backward pass
     double *y;
     const double *dith;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
 
     Df2t f;
     if (FINAL) {
-        const double *s = p.state + static_cast<int64_t>(g) * 5;
+        const double *s = p.zin + static_cast<int64_t>(g) * 5;
         f.z0 = s[0]; f.z1 = s[1]; f.z2 = s[2]; f.z3 = s[3]; f.z4 = s[4];
     } else {
         f.z0 = f.z1 = f.z2 = f.z3 = f.z4 = 0.0;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
     Df2tFused ff;
     if (FINAL) {
         if (have) {
-            const double *s = p.state + g * 5;
+            const double *s = p.zin + g * 5;
             f.z0 = s[0]; f.z1 = s[1]; f.z2 = s[2]; f.z3 = s[3]; f.z4 = s[4];
         }
     } else {
@@ -230,34 +231,63 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
     float *wavp = (FINAL && PASS == 1 && p.wavp) ? p.wavp + p.seg_off[u] + kHalfPad : nullptr;
     for (int sub = 0; sub < kChunk / kTileW; ++sub) {
         // ---- load: row r = chunk sc*32+r, column = lane -----------------------------------------
-        // (the kernel is bound by global-memory latency: on full tiles 16 independent loads are kept
-        // in flight per thread)
-        auto load_row = [&](int r) -> double {
-            const int jr = jt + r * kChunk + sub * kTileW;     // first sample of this row segment
-            const int j = jr + lane;
-            double v = 0.0;
+        // The kernel is bound by global-memory latency, so the loads of a sub-tile must all be in
+        // flight together: on the common path (full tile, every row segment inside the signal) the 32
+        // raw values are fetched branch-free into registers first and only then converted and stored -
+        // a conversion placed right behind its load makes the warp wait for every load in turn.
+        const int jsub = jt + sub * kTileW;
+        bool fast = (rows == 32);
+        if (PASS == 0) fast = fast && (jsub >= kPadLen) && (jsub + 31 * kChunk + kTileW <= kPadLen + L);
+        else fast = fast && (jsub + 31 * kChunk + kTileW <= M);
+        if (fast) {
             if (PASS == 0) {
-                if (jr >= kPadLen && jr + kTileW <= kPadLen + L) {          // interior: plain samples
-                    v = load_sample<DTYPE>(p.x, xbase + (j - kPadLen));
-                } else if (j < M) {
-                    v = ext_sample<DTYPE>(p.x, xbase, L, Lf, j);
+                const int64_t x0 = xbase + (jsub - kPadLen) + lane;
+                if (DTYPE == SSFE_I16) {
+                    const short *xs = static_cast<const short *>(p.x) + x0;
+                    short raw[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) tl[r * kTileStride + lane] = static_cast<double>(raw[r]) * (1.0 / 32768.0);
+                } else if (DTYPE == SSFE_F32) {
+                    const float *xs = static_cast<const float *>(p.x) + x0;
+                    float raw[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) tl[r * kTileStride + lane] = static_cast<double>(raw[r]);
+                } else {
+                    const double *xs = static_cast<const double *>(p.x) + x0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double raw[16];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) raw[r] = xs[(16 * h + r) * kChunk];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) tl[(16 * h + r) * kTileStride + lane] = raw[r];
+                    }
                 }
-            } else if (j < M) {
-                v = y1[M - 1 - j];
-            }
-            return v;
-        };
-        if (rows == 32) {
+            } else {
+                const double *ys = y1 + (M - 1 - jsub - lane);       // reversed: row r is kChunk samples earlier
 #pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 16) {
-                double tmp[16];
+                for (int h = 0; h < 2; ++h) {
+                    double raw[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) tmp[q] = load_row(r0 + q);
+                    for (int r = 0; r < 16; ++r) raw[r] = ys[-(16 * h + r) * kChunk];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) tl[(r0 + q) * kTileStride + lane] = tmp[q];
+                    for (int r = 0; r < 16; ++r) tl[(16 * h + r) * kTileStride + lane] = raw[r];
+                }
             }
         } else {
-            for (int r = 0; r < rows; ++r) tl[r * kTileStride + lane] = load_row(r);
+            for (int r = 0; r < rows; ++r) {
+                const int j = jsub + r * kChunk + lane;
+                double v = 0.0;
+                if (j < M) {
+                    if (PASS == 0) v = ext_sample<DTYPE>(p.x, xbase, L, Lf, j);
+                    else v = y1[M - 1 - j];
+                }
+                tl[r * kTileStride + lane] = v;
+            }
         }
         __syncwarp();
         // ---- recurrence: this lane's chunk is row `lane` -------------------------------------------
@@ -276,25 +306,51 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
         __syncwarp();
         // ---- store (final passes): row-wise again ---------------------------------------------------
         if (FINAL) {
-#pragma unroll 4
-            for (int r = 0; r < rows; ++r) {
-                const int j = jt + r * kChunk + sub * kTileW + lane;
-                if (j >= M) continue;
-                const double y = tl[r * kTileStride + lane];
-                if (PASS == 0) {
-                    y1o[j] = y;
-                } else {
-                    const int nidx = M - 1 - kPadLen - j;
-                    if (nidx >= 0 && nidx < Lf) {
-                        if (p.y) p.y[fbase + nidx] = y;
-                        if (dith) {
-                            const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(dith)[nidx]) : dith[nidx];
-                            const double d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
-                            const double wv = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
-                            if (p.wav64) p.wav64[fbase + nidx] = wv;
-                            const float wf = static_cast<float>(wv);
-                            if (p.wav) p.wav[fbase + nidx] = wf;
-                            if (wavp) wavp[nidx] = wf;
+            bool fast_out = fast;
+            if (PASS == 1) {
+                // all 32 row segments map to output samples (none in the 18-sample pads)
+                const int n_hi = M - 1 - kPadLen - jsub, n_lo = n_hi - 31 * kChunk - (kTileW - 1);
+                fast_out = fast && n_lo >= 0 && n_hi < Lf && dith && p.dith_raw && wavp && !p.y && !p.wav && !p.wav64;
+            }
+            if (fast_out && PASS == 0) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) y1o[jsub + r * kChunk + lane] = tl[r * kTileStride + lane];
+            } else if (fast_out) {
+                // production path of the backward pass: wav = y * 0.96 + (U - 0.5) * 1e-06 -> f32 segment
+                const int n0 = M - 1 - kPadLen - jsub - lane;
+                const uint2 *dr = reinterpret_cast<const uint2 *>(dith) + n0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint2 raw[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) raw[r] = dr[-(16 * h + r) * kChunk];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const double y = tl[(16 * h + r) * kTileStride + lane];
+                        const double d = __dmul_rn(__dsub_rn(mt_raw_to_double(raw[r]), 0.5), c_filt.dither_scale);
+                        wavp[n0 - (16 * h + r) * kChunk] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), d));
+                    }
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const int j = jsub + r * kChunk + lane;
+                    if (j >= M) continue;
+                    const double y = tl[r * kTileStride + lane];
+                    if (PASS == 0) {
+                        y1o[j] = y;
+                    } else {
+                        const int nidx = M - 1 - kPadLen - j;
+                        if (nidx >= 0 && nidx < Lf) {
+                            if (p.y) p.y[fbase + nidx] = y;
+                            if (dith) {
+                                const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(dith)[nidx]) : dith[nidx];
+                                const double d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
+                                const double wv = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
+                                if (p.wav64) p.wav64[fbase + nidx] = wv;
+                                const float wf = static_cast<float>(wv);
+                                if (p.wav) p.wav[fbase + nidx] = wf;
+                                if (wavp) wavp[nidx] = wf;
+                            }
                         }
                     }
                 }
@@ -356,20 +412,31 @@ __global__ void filt_carry_kernel(const FiltParams p)
     dd z[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) z[i] = {__dmul_rn(c_filt.zi[i], x0), 0.0};
+    // one latency chain per utterance: the zero-state finals of the NEXT chunk are fetched while this
+    // chunk's update is computed (separate in / out arrays, so the loads can run ahead of the stores)
+    const double *__restrict__ s_in = p.state + static_cast<int64_t>(c0) * 5;
+    double *__restrict__ zout = p.zin + static_cast<int64_t>(c0) * 5;
+    double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (nc > 1) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) nx[i] = s_in[i];
+    }
     for (int c = 0; c < nc; ++c) {
-        double *s = p.state + static_cast<int64_t>(c0 + c) * 5;
         double sc[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            sc[i] = s[i];
-            s[i] = z[i].hi;                       // z_in of this chunk (hi + lo rounds to hi)
+            sc[i] = nx[i];
+            zout[c * 5 + i] = z[i].hi;            // z_in of this chunk (hi + lo rounds to hi)
         }
         if (c + 1 == nc) break;
+        if (c + 2 < nc) {                         // (the last chunk has no zero-state final)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) nx[i] = s_in[(c + 1) * 5 + i];
+        }
         dd zn[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            // the kernel is a latency chain (one utterance per thread): sum the five products as a
-            // tree, not a chain
+            // sum the five products as a tree, not a chain
             dd pr[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
@@ -471,7 +538,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     const int64_t ext_total = fix_off_host[n] + static_cast<int64_t>(n) * 2 * kPadLen;
     int rc = ensure(ctx, ctx->ws.y1, ext_total * sizeof(double));
     if (rc) return rc;
-    rc = ensure(ctx, ctx->ws.carry, chunks * 5 * sizeof(double));
+    rc = ensure(ctx, ctx->ws.carry, 2 * chunks * 5 * sizeof(double));
     if (rc) return rc;
 
     FiltParams p;
@@ -488,6 +555,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.n_chunks = static_cast<int>(chunks);
     p.chunk_len = sequential ? static_cast<int>(std::min<int64_t>(max_m, 0x7fffffff)) : kChunk;
     p.state = static_cast<double *>(ctx->ws.carry.p);
+    p.zin = p.state + chunks * 5;
     p.y = out.y;
     p.dith = out.dith;
     p.dith_raw = out.dith_raw ? 1 : 0;

@@ -6,10 +6,11 @@
 // stream continues across its files in sorted order, so utterance k starts `skip` doubles in.
 //
 // One CTA per distinct seed walks the stream block by block (624 words).  Word k of the new block
-// depends on new word k-227, so thread t produces words t, t+227, t+454 from the old block and
-// its own results: one __syncthreads() per block (state double-buffered in shared memory).  The
-// 312 doubles of a block are tempered and written coalesced to every request of that seed that
-// overlaps the block.  Streams are independent, so seeds run on different SMs.
+// depends on new word k-227, so thread t produces words t, t+227, t+454 from the old block and its
+// own results: one barrier per block.  The CTA is warp specialised (see mt19937_kernel): a twist
+// group advances the state, an emit group trails through a ring of state blocks and writes the raw
+// word pairs of every requested double; tempering and the conversion to double happen in the
+// consumer (mt_convert.cuh).  Streams are independent, so seeds run on different SMs.
 #include "common.cuh"
 #include "mt_convert.cuh"
 #include <algorithm>
@@ -18,7 +19,7 @@
 namespace ssfe {
 
 constexpr int kMtN = 624, kMtM = 397;
-constexpr int kMtThreads = 320;
+constexpr int kMtThreads = 512;
 
 struct RandJob {
     uint32_t seed;
@@ -36,11 +37,35 @@ __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
-__global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__restrict__ jobs,
-                                                             const RandReq *__restrict__ reqs,
-                                                             uint2 *__restrict__ out)
+// Named-barrier helpers (bar.sync / bar.arrive with an explicit thread count): barrier 0 is
+// __syncthreads(), ids 1.. are ours.
+__device__ __forceinline__ void bar_sync(int id, int count)
 {
-    __shared__ uint32_t s_mt[2][kMtN];
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+constexpr int kMtRing = 4;                       // state blocks in flight between the two warp groups
+constexpr int kMtProd = 256, kMtCons = 256;
+constexpr int kBarFull = 1, kBarEmpty = 1 + kMtRing, kBarProd = 1 + 2 * kMtRing;
+
+// Warp-specialised: warps 0-7 ("twist") only advance the state, one named barrier per block among
+// themselves - that chain (shared-memory load, ~20 integer ops, store, barrier) is the serial
+// bottleneck of a speaker's stream, so nothing else is on it.  Warps 8-15 ("emit") trail behind
+// through a ring of kMtRing state blocks and copy the raw word pairs of every requested double to
+// global memory.  full[slot] / empty[slot] named barriers hand blocks back and forth.
+// Measured on B200: ~300 ns per 624-word block and stream whichever way the hand-off is built
+// (one group + __syncthreads 340 ns, this version 306 ns, mbarrier hand-off 360-380 ns): the floor is
+// the shared-memory round trip plus one CTA-level barrier per block, so a 400-utterance speaker
+// (61.5 k blocks) costs ~20 ms.  It runs on a side stream and is hidden behind the other stages.
+__global__ void __launch_bounds__(kMtProd + kMtCons) mt19937_kernel(const RandJob *__restrict__ jobs,
+                                                                    const RandReq *__restrict__ reqs,
+                                                                    uint2 *__restrict__ out)
+{
+    __shared__ __align__(16) uint32_t s_mt[kMtRing][kMtN];
     const RandJob job = jobs[blockIdx.x];
     const RandReq *rq = reqs + job.first_req;
     const int tid = threadIdx.x;
@@ -56,64 +81,80 @@ __global__ void __launch_bounds__(kMtThreads) mt19937_kernel(const RandJob *__re
     __syncthreads();
 
     const uint64_t last_double = rq[job.n_req - 1].skip + static_cast<uint64_t>(rq[job.n_req - 1].count);
-    const uint64_t n_blocks = (last_double + 311) / 312;   // blocks of 312 doubles to generate
-    // current request, cached in registers (all threads walk the request list in lock step)
-    int r0 = 0;
-    uint64_t r_beg = rq[0].skip, r_end = rq[0].skip + static_cast<uint64_t>(rq[0].count);
-    int64_t r_out = rq[0].out_off;
-    int cur = 0;
-    for (uint64_t blk = 0; blk < n_blocks; ++blk) {
-        const uint32_t *o = s_mt[cur];
-        uint32_t *nw = s_mt[cur ^ 1];
-        // The twist of word k needs the NEW word k-227, and 3 * 227 > 624: thread t produces words
-        // t, t+227 and t+454 from the old block and its own results, so one barrier per block is enough.
-        if (tid < 227) {
-            const uint32_t n0 = o[tid + kMtM] ^ mt_mix(o[tid], o[tid + 1]);
-            const uint32_t n1 = n0 ^ mt_mix(o[tid + 227], o[tid + 228]);
-            nw[tid] = n0;
-            nw[tid + 227] = n1;
-            if (tid < 169) {
-                nw[tid + 454] = n1 ^ mt_mix(o[tid + 454], o[tid + 455]);
-            } else if (tid == 169) {   // word 623 wraps around to the new word 0 (recomputed here)
-                const uint32_t new0 = o[kMtM] ^ mt_mix(o[0], o[1]);
-                nw[623] = n1 ^ mt_mix(o[623], new0);
-            }
-        }
-        __syncthreads();
-        cur ^= 1;
+    const long long n_blocks = static_cast<long long>((last_double + 311) / 312);   // data blocks 1..n_blocks
 
-        const uint64_t d0 = blk * 312;                     // first double of this block
-        while (r0 < job.n_req && r_end <= d0) {
-            ++r0;
-            if (r0 < job.n_req) {
-                r_beg = rq[r0].skip;
-                r_end = r_beg + static_cast<uint64_t>(rq[r0].count);
-                r_out = rq[r0].out_off;
+    if (tid < kMtProd) {
+        // ---- twist group --------------------------------------------------------------------------
+        for (long long B = 1; B <= n_blocks; ++B) {
+            const int slot = static_cast<int>(B & (kMtRing - 1));
+            const uint32_t *o = s_mt[(B - 1) & (kMtRing - 1)];
+            uint32_t *nw = s_mt[slot];
+            // slot held data block B - kMtRing: wait until the emit group is done with it
+            if (B >= kMtRing + 1) bar_sync(kBarEmpty + slot, kMtProd + kMtCons);
+            // Word k of the new block needs the NEW word k-227 and 3 * 227 > 624: thread t produces
+            // words t, t+227, t+454 from the old block and its own results - no barrier in between.
+            if (tid < 227) {
+                const uint32_t n0 = o[tid + kMtM] ^ mt_mix(o[tid], o[tid + 1]);
+                const uint32_t n1 = n0 ^ mt_mix(o[tid + 227], o[tid + 228]);
+                nw[tid] = n0;
+                nw[tid + 227] = n1;
+                if (tid < 169) {
+                    nw[tid + 454] = n1 ^ mt_mix(o[tid + 454], o[tid + 455]);
+                } else if (tid == 169) {   // word 623 wraps around to the new word 0 (recomputed here)
+                    const uint32_t new0 = o[kMtM] ^ mt_mix(o[0], o[1]);
+                    nw[623] = n1 ^ mt_mix(o[623], new0);
+                }
             }
+            // block B complete for the twist group (the barrier also drains the shared-memory stores),
+            // then published to the emit group
+            bar_sync(kBarProd, kMtProd);
+            bar_arrive(kBarFull + slot, kMtProd + kMtCons);
         }
-        if (r0 < job.n_req && tid < 312) {
-            if (r_beg <= d0 && d0 + 312 <= r_end) {
-                // common case: the whole block belongs to the current request
-                out[r_out + static_cast<int64_t>(d0 - r_beg) + tid] = *reinterpret_cast<const uint2 *>(nw + 2 * tid);
-            } else if (r_beg < d0 + 312) {
-                const uint64_t d = d0 + tid;
-                uint64_t b = r_beg, e = r_end;
-                int64_t oo = r_out;
-                int r = r0;
-                while (r < job.n_req && e <= d) {          // the block spans a request boundary
-                    ++r;
-                    if (r < job.n_req) {
-                        b = rq[r].skip;
-                        e = b + static_cast<uint64_t>(rq[r].count);
-                        oo = rq[r].out_off;
+    } else {
+        // ---- emit group ---------------------------------------------------------------------------
+        const int ct = tid - kMtProd;
+        int r0 = 0;
+        uint64_t r_beg = rq[0].skip, r_end = rq[0].skip + static_cast<uint64_t>(rq[0].count);
+        int64_t r_out = rq[0].out_off;
+        for (long long B = 1; B <= n_blocks; ++B) {
+            const int slot = static_cast<int>(B & (kMtRing - 1));
+            bar_sync(kBarFull + slot, kMtProd + kMtCons);
+            const uint32_t *nw = s_mt[slot];
+            const uint64_t d0 = static_cast<uint64_t>(B - 1) * 312;   // first double of this block
+            while (r0 < job.n_req && r_end <= d0) {
+                ++r0;
+                if (r0 < job.n_req) {
+                    r_beg = rq[r0].skip;
+                    r_end = r_beg + static_cast<uint64_t>(rq[r0].count);
+                    r_out = rq[r0].out_off;
+                }
+            }
+            if (r0 < job.n_req) {
+                for (int t = ct; t < 312; t += kMtCons) {
+                    if (r_beg <= d0 && d0 + 312 <= r_end) {
+                        // common case: the whole block belongs to the current request
+                        out[r_out + static_cast<int64_t>(d0 - r_beg) + t] = *reinterpret_cast<const uint2 *>(nw + 2 * t);
+                    } else if (r_beg < d0 + 312) {
+                        const uint64_t d = d0 + t;
+                        uint64_t b = r_beg, e = r_end;
+                        int64_t oo = r_out;
+                        int r = r0;
+                        while (r < job.n_req && e <= d) {      // the block spans a request boundary
+                            ++r;
+                            if (r < job.n_req) {
+                                b = rq[r].skip;
+                                e = b + static_cast<uint64_t>(rq[r].count);
+                                oo = rq[r].out_off;
+                            }
+                        }
+                        if (r < job.n_req && d >= b)
+                            out[oo + static_cast<int64_t>(d - b)] = *reinterpret_cast<const uint2 *>(nw + 2 * t);
                     }
                 }
-                if (r < job.n_req && d >= b)     // raw word pair; tempering + conversion happen in the consumer
-                    out[oo + static_cast<int64_t>(d - b)] = *reinterpret_cast<const uint2 *>(nw + 2 * tid);
             }
+            // hand the slot back if the twist group will reuse it (data block B + kMtRing)
+            if (B + kMtRing <= n_blocks) bar_arrive(kBarEmpty + slot, kMtProd + kMtCons);
         }
-        // no second barrier: the next twist writes the buffer whose last readers passed the barrier
-        // above, and only reads the buffer this output phase reads.
     }
 }
 

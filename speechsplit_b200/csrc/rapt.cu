@@ -94,15 +94,18 @@ struct RaptParams {
 
 // ---- K1 ------------------------------------------------------------------------------------
 // 256 consecutive 2 kHz outputs of one utterance per CTA (n_ds is padded to a multiple of 256).  The
-// 2121 input samples are staged once, scaled by 32768, in shared memory with one pad word per 32 so
-// that the stride-8 tap reads of a warp fall in distinct banks.
+// 2121 input samples are staged once, scaled by 32768, in shared memory as 8 phase rows: sample i
+// sits at row i % 8, column i / 8.  Output t needs samples 8 t + j, i.e. row j % 8, column t + j / 8:
+// for a fixed tap the threads of a warp read consecutive words (no conflicts, immediate offsets).
+// The row pitch is 4 mod 32 so that the coalesced staging stores (8 rows x 4 columns per warp) hit
+// 32 different banks as well.
 constexpr int kDecTile = 256;
 constexpr int kDecIn = kDec * (kDecTile - 1) + kNco;          // 2121
-__device__ __forceinline__ int dec_skew(int i) { return i + (i >> 5); }
+constexpr int kDecPitch = 292;                                // >= 266 columns, == 4 (mod 32)
 
 __global__ void __launch_bounds__(kDecTile) rapt_decimate_kernel(const RaptParams p)
 {
-    __shared__ float s_x[kDecIn + kDecIn / 32 + 2];
+    __shared__ float s_x[kDec * kDecPitch];
     const long long gid0 = blockIdx.x * static_cast<long long>(kDecTile);
     const int u = find_segment(p.ds_offs, p.n, gid0);
     const RaptUtt ut = p.utts[u];
@@ -111,13 +114,13 @@ __global__ void __launch_bounds__(kDecTile) rapt_decimate_kernel(const RaptParam
     const int base = kDec * m0 - (kNco / 2);
     for (int i = threadIdx.x; i < kDecIn; i += kDecTile) {
         const int idx = base + i;
-        s_x[dec_skew(i)] = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+        s_x[(i & (kDec - 1)) * kDecPitch + (i >> 3)] = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
     }
     __syncthreads();
-    const int t8 = kDec * threadIdx.x;
+    const float *col = s_x + threadIdx.x;
     float sum = 0.0f;
-#pragma unroll 9
-    for (int j = 0; j < kNco; ++j) sum += c_rapt.co[j] * s_x[dec_skew(t8 + j)];
+#pragma unroll
+    for (int j = 0; j < kNco; ++j) sum += c_rapt.co[j] * col[(j & (kDec - 1)) * kDecPitch + (j >> 3)];
     p.ds[gid0 + threadIdx.x] =
         static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
 }

@@ -39,3 +39,26 @@ def lpt_shards(lengths: Sequence[int], n_shards: int) -> List[np.ndarray]:
         owner[i] = k
         load[k] += lengths[i]
     return [np.nonzero(owner == k)[0] for k in range(n_shards)]
+
+
+def lpt_shards_by_speaker(speakers: Sequence[str], lengths: Sequence[int], n_shards: int) -> List[np.ndarray]:
+    """Speaker-atomic variant: whole speakers are dealt to shards, longest first.
+
+    A speaker's MT19937 dither stream is sequential, so a shard that owns only some of a speaker's
+    files still has to walk that stream up to its last file.  Keeping speakers whole means every
+    stream is generated on exactly one GPU (SURVEY.md 8(e) option 1).  With 109 speakers on 8 GPUs
+    the imbalance is at most one speaker (~3 %)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    spk = np.asarray(speakers)
+    names, inv = np.unique(spk, return_inverse=True)
+    if len(names) < n_shards:           # fewer speakers than shards: fall back to utterance granularity
+        return lpt_shards(lengths, n_shards)
+    totals = np.bincount(inv, weights=lengths, minlength=len(names))
+    owner_of_spk = np.empty(len(names), dtype=np.int64)
+    load = np.zeros(n_shards)
+    for k in np.argsort(-totals, kind="stable"):
+        j = int(np.argmin(load))
+        owner_of_spk[k] = j
+        load[j] += totals[k]
+    owner = owner_of_spk[inv]
+    return [np.nonzero(owner == k)[0] for k in range(n_shards)]

@@ -10,7 +10,7 @@ import pytest
 from numpy.random import RandomState
 
 from speechsplit_b200.corpus import make_manifest
-from speechsplit_b200.sharding import dither_skips, fixed_length, lpt_shards
+from speechsplit_b200.sharding import dither_skips, fixed_length, lpt_shards, lpt_shards_by_speaker
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -48,6 +48,26 @@ def test_lpt_shards_partition_and_balance(world):
     assert loads.max() - loads.min() <= lengths.max()                   # LPT bound
     for s in shards:
         assert np.all(np.diff(s) > 0)                                   # corpus order kept inside a shard
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_speaker_atomic_shards(world):
+    metas = make_manifest(109, 12, seed=3)
+    spk = [m.spk for m in metas]
+    lengths = np.array([m.length for m in metas])
+    shards = lpt_shards_by_speaker(spk, lengths, world)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(len(metas)))
+    owner = {}
+    for k, s in enumerate(shards):
+        for i in s:
+            assert owner.setdefault(spk[i], k) == k            # a speaker lives on exactly one shard
+        assert np.all(np.diff(s) > 0)
+    loads = np.array([lengths[s].sum() for s in shards], dtype=float)
+    assert loads.max() / loads.mean() < 1.08
+    # fewer speakers than shards: falls back to utterance granularity
+    few = make_manifest(2, 10, seed=1)
+    sh = lpt_shards_by_speaker([m.spk for m in few], [m.length for m in few], 4)
+    assert sorted(np.concatenate(sh).tolist()) == list(range(20)) and all(len(x) for x in sh)
 
 
 WORKER = r"""
