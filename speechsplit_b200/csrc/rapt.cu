@@ -112,9 +112,19 @@ __global__ void __launch_bounds__(kDecTile) rapt_decimate_kernel(const RaptParam
     const int m0 = static_cast<int>(gid0 - ut.ds_off);
     const float *x = p.wav + ut.wav_off;
     const int base = kDec * m0 - (kNco / 2);
-    for (int i = threadIdx.x; i < kDecIn; i += kDecTile) {
-        const int idx = base + i;
-        s_x[(i & (kDec - 1)) * kDecPitch + (i >> 3)] = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+    {   // all loads of a thread in flight together (clamped index, select afterwards)
+        constexpr int kPer = (kDecIn + kDecTile - 1) / kDecTile;     // 9
+        float raw[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int idx = base + threadIdx.x + q * kDecTile;
+            raw[q] = x[min(max(idx, 0), ut.L - 1)];
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int i = threadIdx.x + q * kDecTile, idx = base + i;
+            if (i < kDecIn) s_x[(i & (kDec - 1)) * kDecPitch + (i >> 3)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+        }
     }
     __syncthreads();
     const float *col = s_x + threadIdx.x;
@@ -308,7 +318,14 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
     {
         const int start0 = cf.start, nlags0 = cf.nlags, total = cf.ncomp;   // size + nlags0 + start0
         const float *fx = x + static_cast<long long>(g) * kHop;
-        for (int t = lane; t < total; t += 32) db[t] = fx[t] * 32768.0f;
+        {
+            float raw[14];
+#pragma unroll
+            for (int q = 0; q < 14; ++q) raw[q] = fx[min(lane + 32 * q, total - 1)];
+#pragma unroll
+            for (int q = 0; q < 14; ++q)
+                if (lane + 32 * q < total) db[lane + 32 * q] = raw[q] * 32768.0f;
+        }
         for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;
         __syncwarp();
         float engr = 0.0f;
@@ -455,9 +472,18 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     const int g0 = (static_cast<int>(blockIdx.x) - tile_off[u]) * kStatFrames;
     const float *x = p.wav + ut.wav_off;
     const int s_lo = kHop * g0 - (kStatGap + 80);
-    for (int i = tid; i < kStatSpan; i += 2 * kStatFrames) {
-        const int idx = s_lo + i;
-        s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+    for (int i0 = 0; i0 < kStatSpan; i0 += 16 * 2 * kStatFrames) {   // 16 loads in flight per thread
+        float raw[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int idx = s_lo + i0 + tid + q * 2 * kStatFrames;
+            raw[q] = x[min(max(idx, 0), ut.L - 1)];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int i = i0 + tid + q * 2 * kStatFrames, idx = s_lo + i;
+            if (i < kStatSpan) s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+        }
     }
     for (int i = tid; i < kStatW; i += 2 * kStatFrames) {
         s_w479[i] = (i < kStatW - 1) ? p.w479[i] : 0.0f;
