@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--parity-utts", type=int, default=12)
+    ap.add_argument("--workload", default="vctk", choices=["vctk", "longform", "single", "collate"],
+                    help="vctk = BASELINE configs[1]/[2] (the bench line); longform = configs[3] (256 x 60 s); "
+                         "single = configs[0] (one 3 s male utterance); collate = configs[4] (batch-16 training crops)")
     return ap.parse_args()
 
 
@@ -169,7 +172,12 @@ def build_shard(args, rank, world):
     """Manifest -> LPT shard of this rank -> control tracks (process pool, before CUDA is touched)."""
     from speechsplit_b200.corpus import control_tracks, make_manifest
     from speechsplit_b200.sharding import dither_skips, lpt_shards_by_speaker
-    metas = make_manifest(args.speakers, args.utts, seed=0)
+    if args.workload == "longform":       # configs[3]: 4 speakers x 64 utterances of 60.000 s
+        metas = make_manifest(4, 64, seed=0, fixed_len=960000)
+    elif args.workload == "single":       # configs[0]: one 3 s male utterance (p226)
+        metas = make_manifest(1, 1, first_id=226, seed=0, fixed_len=48000)
+    else:
+        metas = make_manifest(args.speakers, args.utts, seed=0)
     skips = dither_skips([m.spk for m in metas], [m.length for m in metas])
     shard = lpt_shards_by_speaker([m.spk for m in metas], [m.length for m in metas], world)[rank]
     mine = [metas[i] for i in shard]
@@ -301,6 +309,32 @@ def run_ours(args):
         e2e["matches_device_path"] = same
         del xh, ho
 
+    collate = None
+    if args.workload == "collate" and rank == 0:
+        # configs[4]: batch 16 of 64..128-frame crops -> mel (16,192,80) clipped + one-hot (16,192,257)
+        rng = np.random.default_rng(0)
+        frs = np.diff(fr)
+        cand = np.nonzero(frs > 130)[0]
+
+        def crop_step():
+            utt = rng.choice(cand, 16)
+            ln = rng.integers(64, 129, 16)
+            left = np.array([rng.integers(0, frs[u] - l) for u, l in zip(utt, ln)])
+            return fe.collate(outs["mel"], outs["f0_norm"], fr, utt, left, ln, 192)
+
+        for _ in range(20):
+            crop_step()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        c0.record()
+        for _ in range(200):
+            crop_step()
+        c1.record()
+        torch.cuda.synchronize()
+        collate = {"steps_per_s_device": 200 / (c0.elapsed_time(c1) * 1e-3), "steps_per_s_wall": 200 / (time.perf_counter() - t0),
+                   "batch": 16, "max_len_pad": 192}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -352,6 +386,12 @@ def run_ours(args):
                        "collective": "none on the data path"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "stage_ms": stages, "parity": parity}
+    if args.workload != "vctk":
+        line["config"]["workload"] = {"longform": "BASELINE configs[3]: 256 x 60.000 s utterances (4 speakers x 64)",
+                                      "single": "BASELINE configs[0]: one 3 s male utterance (p226)",
+                                      "collate": line["config"]["workload"] + " + configs[4] collator"}[args.workload]
+    if collate:
+        line["collate"] = collate
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
         mbar_wait(&ws.bar, parity);
         parity ^= 1;
         float2 v[32];
+        // (Re-using frame A's reads for frame B - sample m of B is sample m+8 of A, 40 reads instead of
+        // 64 - was measured 4 % slower: the longer live ranges cost more than the 24 wavefronts saved.)
         if (cur.has_b) {
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
@@ -204,6 +206,9 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
         }
 
         fft32_dif(v);
+        // inter-pass twiddles W_1024^(lane k1) from the [k1][lane] table.  (Building them from five
+        // table reads by complex products was measured: -52 shared-memory wavefronts per pair but +100
+        // FP32 instructions made the kernel 7 % slower - issue and shared memory are balanced here.)
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
             const int k1 = bitrev5(r);
