@@ -34,3 +34,40 @@ extern "C" void ssfe_filt_power_dd(const double *a6, int power, double *hi25, do
         lo25[i] = (double)(R[i] - (q)h);
     }
 }
+
+// P[j] = A^(base * j) for j = 1..count, each as [hi 25][lo 25]; out holds (count + 1) * 50 doubles and
+// entry 0 is left zero.  M = A^base by repeated multiplication, then P[j] = P[j-1] M, all in 113 bits.
+extern "C" void ssfe_filt_power_table_dd(const double *a6, int base, int count, double *out)
+{
+    typedef __float128 q;
+    q A[25], M[25], P[25], T[25];
+    for (int i = 0; i < 25; ++i) A[i] = 0;
+    for (int i = 0; i < 5; ++i) {
+        A[i * 5 + 0] = -(q)a6[i + 1];
+        if (i + 1 < 5) A[i * 5 + i + 1] = 1;
+    }
+    auto mul = [](const q *X, const q *Y, q *Z) {
+        for (int i = 0; i < 5; ++i)
+            for (int j = 0; j < 5; ++j) {
+                q acc = 0;
+                for (int k = 0; k < 5; ++k) acc += X[i * 5 + k] * Y[k * 5 + j];
+                Z[i * 5 + j] = acc;
+            }
+    };
+    for (int i = 0; i < 25; ++i) M[i] = (i % 6 == 0) ? 1 : 0;
+    for (int s = 0; s < base; ++s) {
+        mul(A, M, T);
+        std::memcpy(M, T, sizeof(M));
+    }
+    std::memcpy(P, M, sizeof(P));
+    for (int i = 0; i < 50; ++i) out[i] = 0.0;
+    for (int j = 1; j <= count; ++j) {
+        for (int i = 0; i < 25; ++i) {
+            const double h = (double)P[i];
+            out[j * 50 + i] = h;
+            out[j * 50 + 25 + i] = (double)(P[i] - (q)h);
+        }
+        mul(P, M, T);
+        std::memcpy(P, T, sizeof(P));
+    }
+}

@@ -28,10 +28,16 @@
 namespace ssfe {
 
 extern "C" void ssfe_filt_power_dd(const double *a6, int power, double *hi25, double *lo25);   // filt_consts.cpp
+extern "C" void ssfe_filt_power_table_dd(const double *a6, int base, int count, double *out);
 
 constexpr int kChunk = 256;
 constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
 constexpr int kFiltThreads = 128;
+// Utterances of at least this many chunks (>= 4.1 s) take the warp-parallel carry, shorter ones the
+// thread-per-utterance carry: the scan does 7x the arithmetic, which only pays when the chain is long.
+// The rule depends on the utterance alone, never on the batch, so results stay batch independent.
+constexpr int kWarpCarryMin = 256;
+
 
 struct FiltConsts {
     double b[6], a[6], zi[5];
@@ -401,6 +407,7 @@ __global__ void filt_carry_kernel(const FiltParams p)
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= p.n) return;
     const int c0 = p.chunk_off[u], nc = p.chunk_off[u + 1] - c0;
+    if (p.chunk_len == kChunk && nc >= kWarpCarryMin) return;      // long utterances: filt_carry_warp_kernel
     const int64_t L = p.in_off[u + 1] - p.in_off[u];
     const int64_t fbase = p.fix_off[u];
     const int64_t Lf = p.fix_off[u + 1] - fbase;
@@ -452,6 +459,102 @@ __global__ void filt_carry_kernel(const FiltParams p)
     }
 }
 
+// ---- warp-parallel carry ----------------------------------------------------------------------------
+// The thread-per-utterance carry above is one latency chain of (chunks) double-double mat-vecs: 188 for
+// a 3 s utterance, 3751 for a 60 s one (26 ms per pass).  Here a WARP owns an utterance: lane = chunk
+// inside a tile of 32, and the recurrence z[c+1] = M z[c] + s[c] (M = A^256) is solved per tile by a
+// Kogge-Stone scan over the lanes with the precomputed powers P[j] = M^j, j = 1..32 (double-double,
+// formed in __float128 on the host):
+//     v[c] <- v[c] + P[d] v[c-d]   for d = 1, 2, 4, 8, 16       ->  v[c] = sum_{i<=c} M^(c-i) s[i]
+//     z_in[c] = P[c] z0 + v[c-1]   (z_in[0] = z0),   next tile's z0 = P[32] z0 + v[31]
+// 7 mat-vecs of depth per tile instead of 32, and no dependence on the batch: the same utterance gives
+// bit-identical results in any batch (the strategy is fixed, not chosen by batch size).
+__device__ __forceinline__ void dd_matvec(const double *__restrict__ P, const dd (&z)[5], dd (&out)[5])
+{
+    // P: [2][25] (hi then lo), row-major
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        dd pr[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) pr[k] = dd_mul(dd{P[i * 5 + k], P[25 + i * 5 + k]}, z[k]);
+        out[i] = dd_add(dd_add(dd_add(pr[0], pr[1]), dd_add(pr[2], pr[3])), pr[4]);
+    }
+}
+__device__ __forceinline__ dd dd_shfl(dd v, int src)
+{
+    return {__shfl_sync(0xffffffffu, v.hi, src), __shfl_sync(0xffffffffu, v.lo, src)};
+}
+__device__ __forceinline__ dd dd_shfl_up(dd v, int d)
+{
+    return {__shfl_up_sync(0xffffffffu, v.hi, d), __shfl_up_sync(0xffffffffu, v.lo, d)};
+}
+
+constexpr int kCarryWarps = 4;
+
+template <int DTYPE, int PASS>
+__global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_warp_kernel(const FiltParams p,
+                                                                           const double *__restrict__ pw /* [33][50] */)
+{
+    const int lane = threadIdx.x & 31;
+    const int u = blockIdx.x * kCarryWarps + (threadIdx.x >> 5);
+    if (u >= p.n) return;
+    const int c0 = p.chunk_off[u], nc = p.chunk_off[u + 1] - c0;
+    if (nc < kWarpCarryMin) return;
+    const int64_t L = p.in_off[u + 1] - p.in_off[u];
+    const int64_t fbase = p.fix_off[u];
+    const int64_t Lf = p.fix_off[u + 1] - fbase;
+    const int64_t M = Lf + 2 * kPadLen;
+    const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
+    double x0;
+    if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
+    else x0 = p.y1[ebase + M - 1];
+    dd z0[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z0[i] = {__dmul_rn(c_filt.zi[i], x0), 0.0};
+    const double *__restrict__ s_in = p.state + static_cast<int64_t>(c0) * 5;
+    double *__restrict__ zout = p.zin + static_cast<int64_t>(c0) * 5;
+
+    for (int t0 = 0; t0 < nc; t0 += 32) {
+        const int c = t0 + lane;
+        dd v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = {(c + 1 < nc) ? s_in[c * 5 + i] : 0.0, 0.0};   // last chunk: no final
+        // inclusive scan over the tile
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            dd up[5], mv[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) up[i] = dd_shfl_up(v[i], d);
+            dd_matvec(pw + d * 50, up, mv);
+            if (lane >= d) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) v[i] = dd_add(v[i], mv[i]);
+            }
+        }
+        // chunk-entry states
+        dd e[5], pz[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) e[i] = dd_shfl_up(v[i], 1);
+        dd_matvec(pw + max(lane, 1) * 50, z0, pz);
+        if (c < nc) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const dd zi = (lane == 0) ? z0[i] : dd_add(pz[i], e[i]);
+                zout[c * 5 + i] = zi.hi;
+            }
+        }
+        // carry into the next tile
+        if (t0 + 32 < nc) {
+            dd last[5], nz[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) last[i] = dd_shfl(v[i], 31);
+            dd_matvec(pw + 32 * 50, z0, nz);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) z0[i] = dd_add(nz[i], last[i]);
+        }
+    }
+}
+
 // reflect edges of the padded segments once the interior is written (np.pad 'reflect', utils.py:20)
 __global__ void reflect_edges_kernel(float *__restrict__ wavp, const int64_t *__restrict__ seg_off,
                                      const int64_t *__restrict__ fix_off, int n)
@@ -481,7 +584,7 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 
 template <int DTYPE>
 static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready, bool keep_dith,
-                          const int *tile_off, int n_tiles)
+                          const int *tile_off, int n_tiles, bool any_long)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
@@ -491,8 +594,13 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
         filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
         SSFE_LAUNCHED(ctx);
     }
+    const unsigned gw = (p.n + kCarryWarps - 1) / kCarryWarps;
     filt_carry_kernel<DTYPE, 0><<<gu, 64, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
+    if (!sequential && any_long) {
+        filt_carry_warp_kernel<DTYPE, 0><<<gw, kCarryWarps * 32, 0, st>>>(p, ctx->d_filt);
+        SSFE_LAUNCHED(ctx);
+    }
     if (sequential) filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
     else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
     SSFE_LAUNCHED(ctx);
@@ -503,6 +611,10 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     }
     filt_carry_kernel<DTYPE, 1><<<gu, 64, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
+    if (!sequential && any_long) {
+        filt_carry_warp_kernel<DTYPE, 1><<<gw, kCarryWarps * 32, 0, st>>>(p, ctx->d_filt);
+        SSFE_LAUNCHED(ctx);
+    }
     if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
     if (sequential) filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
     else filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
@@ -518,6 +630,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     const bool sequential = ctx->cfg.filtfilt_mode == 1;
     std::vector<int> chunk_off(n + 1), tile_off(n + 1);
     int64_t chunks = 0, max_m = 0, tiles = 0;
+    bool any_long = false;
     for (int i = 0; i < n; ++i) {
         const int64_t Lf = fix_off_host[i + 1] - fix_off_host[i];
         if (Lf <= kPadLen)
@@ -529,6 +642,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
         chunk_off[i] = static_cast<int>(chunks);
         tile_off[i] = static_cast<int>(tiles);
         const int64_t nc = sequential ? 1 : (M + kChunk - 1) / kChunk;
+        any_long = any_long || nc >= kWarpCarryMin;
         chunks += nc;
         tiles += (nc + 31) / 32;
         if (chunks > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (chunks)");
@@ -565,9 +679,9 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.wav64 = out.wav64;
     p.y1_out = static_cast<double *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles, any_long);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles, any_long);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles, any_long);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }
@@ -582,12 +696,22 @@ int init_filtfilt(ssfe_ctx *ctx)
     }
     for (int i = 0; i < 5; ++i) c.zi[i] = ctx->cfg.zi[i];
     ssfe_filt_power_dd(c.a, kChunk, c.m_hi, c.m_lo);
+    {   // P[j] = A^(kChunk * j), j = 1..32, for the warp-parallel carry
+        std::vector<double> pw(33 * 50, 0.0);
+        ssfe_filt_power_table_dd(c.a, kChunk, 32, pw.data());
+        SSFE_CUDA(ctx, cudaMalloc(&ctx->d_filt, pw.size() * sizeof(double)));
+        SSFE_CUDA(ctx, cudaMemcpy(ctx->d_filt, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     c.wav_scale = ctx->cfg.wav_scale;
     c.dither_scale = ctx->cfg.dither_scale;
     SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_filt, &c, sizeof(c)));
     return SSFE_OK;
 }
 
-void free_filtfilt(ssfe_ctx *) {}
+void free_filtfilt(ssfe_ctx *ctx)
+{
+    cudaFree(ctx->d_filt);
+    ctx->d_filt = nullptr;
+}
 
 }  // namespace ssfe
