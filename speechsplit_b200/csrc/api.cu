@@ -213,6 +213,7 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_dith_free, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_mt_go, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         ctx->stream = ctx->own_stream;
         if ((rc = init_stft_tables(ctx))) break;
         if ((rc = init_filtfilt(ctx))) break;
@@ -254,7 +255,7 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
         for (cudaEvent_t e : row)
             if (e) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
-    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->aux_free[0], ctx->aux_free[1], ctx->ev_h2d[0],
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1], ctx->ev_h2d[0],
                           ctx->ev_h2d[1], ctx->ev_comp[0], ctx->ev_comp[1], ctx->ev_d2h[0], ctx->ev_d2h[1]})
         if (e) cudaEventDestroy(e);
     for (auto &row : ctx->ev_auxr)

@@ -52,10 +52,12 @@ struct ssfe_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     cudaEvent_t ev_dith_free = nullptr;                       // recorded after the kernel that reads `dith`
+    cudaEvent_t ev_mt_go = nullptr;                           // recorded where the NEXT call's dither walk may start
     char *aux_host[2] = {nullptr, nullptr}, *aux_dev[2] = {nullptr, nullptr};   // side-stream metadata staging
     size_t aux_cap[2] = {0, 0};
     cudaEvent_t aux_free[2] = {nullptr, nullptr};
     int aux_idx = 0;
+    bool mt_attr_set = false;
     ssfe_config cfg;
     std::vector<float> mel_basis;      // host copy (513 x 80)
     char err[512];

@@ -193,6 +193,10 @@ struct Df2tFused {
     }
 };
 
+template <int DTYPE, int PASS> struct RawType { using T = double; };
+template <> struct RawType<SSFE_I16, 0> { using T = short; };
+template <> struct RawType<SSFE_F32, 0> { using T = float; };
+
 template <int DTYPE, int PASS, bool FINAL>
 __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
                                                                      int n_tiles)
@@ -235,54 +239,42 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
     double *y1o = FINAL ? p.y1_out + ebase : nullptr;
     const double *dith = (FINAL && PASS == 1 && p.dith) ? p.dith + fbase : nullptr;
     float *wavp = (FINAL && PASS == 1 && p.wavp) ? p.wavp + p.seg_off[u] + kHalfPad : nullptr;
+    // ---- load machinery -------------------------------------------------------------------------------
+    // The kernel is bound by global-memory latency.  (1) On the common path (full tile, every row
+    // segment inside the signal) the 32 raw values of a sub-tile are fetched branch-free into registers
+    // and only later converted and stored - a conversion placed right behind its load makes the
+    // in-order warp wait for every load in turn.  (2) The fetch for sub-tile s+1 is issued BEFORE the
+    // recurrence of sub-tile s runs, so the ~1-2 us of DRAM latency hide behind ~2000 cycles of fp64.
+    using RawT = typename RawType<DTYPE, PASS>::T;
+    RawT raw[32];
+    auto is_fast = [&](int sub) -> bool {
+        const int js = jt + sub * kTileW;
+        if (rows != 32) return false;
+        if (PASS == 0) return (js >= kPadLen) && (js + 31 * kChunk + kTileW <= kPadLen + L);
+        return js + 31 * kChunk + kTileW <= M;
+    };
+    auto issue = [&](int sub) {
+        const int js = jt + sub * kTileW;
+        if (PASS == 0) {
+            const RawT *xs = static_cast<const RawT *>(p.x) + (xbase + (js - kPadLen) + lane);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
+        } else {
+            const double *ys = y1 + (M - 1 - js - lane);             // reversed: row r is kChunk samples earlier
+#pragma unroll
+            for (int r = 0; r < 32; ++r) raw[r] = static_cast<RawT>(ys[-r * kChunk]);
+        }
+    };
+    if (is_fast(0)) issue(0);
     for (int sub = 0; sub < kChunk / kTileW; ++sub) {
-        // ---- load: row r = chunk sc*32+r, column = lane -----------------------------------------
-        // The kernel is bound by global-memory latency, so the loads of a sub-tile must all be in
-        // flight together: on the common path (full tile, every row segment inside the signal) the 32
-        // raw values are fetched branch-free into registers first and only then converted and stored -
-        // a conversion placed right behind its load makes the warp wait for every load in turn.
         const int jsub = jt + sub * kTileW;
-        bool fast = (rows == 32);
-        if (PASS == 0) fast = fast && (jsub >= kPadLen) && (jsub + 31 * kChunk + kTileW <= kPadLen + L);
-        else fast = fast && (jsub + 31 * kChunk + kTileW <= M);
+        const bool fast = is_fast(sub);
         if (fast) {
-            if (PASS == 0) {
-                const int64_t x0 = xbase + (jsub - kPadLen) + lane;
-                if (DTYPE == SSFE_I16) {
-                    const short *xs = static_cast<const short *>(p.x) + x0;
-                    short raw[32];
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) tl[r * kTileStride + lane] = static_cast<double>(raw[r]) * (1.0 / 32768.0);
-                } else if (DTYPE == SSFE_F32) {
-                    const float *xs = static_cast<const float *>(p.x) + x0;
-                    float raw[32];
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) tl[r * kTileStride + lane] = static_cast<double>(raw[r]);
-                } else {
-                    const double *xs = static_cast<const double *>(p.x) + x0;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        double raw[16];
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) raw[r] = xs[(16 * h + r) * kChunk];
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) tl[(16 * h + r) * kTileStride + lane] = raw[r];
-                    }
-                }
-            } else {
-                const double *ys = y1 + (M - 1 - jsub - lane);       // reversed: row r is kChunk samples earlier
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double raw[16];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) raw[r] = ys[-(16 * h + r) * kChunk];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) tl[(16 * h + r) * kTileStride + lane] = raw[r];
-                }
+            for (int r = 0; r < 32; ++r) {
+                double v = static_cast<double>(raw[r]);
+                if (PASS == 0 && DTYPE == SSFE_I16) v *= (1.0 / 32768.0);
+                tl[r * kTileStride + lane] = v;
             }
         } else {
             for (int r = 0; r < rows; ++r) {
@@ -295,6 +287,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
                 tl[r * kTileStride + lane] = v;
             }
         }
+        if (sub + 1 < kChunk / kTileW && is_fast(sub + 1)) issue(sub + 1);     // in flight during the recurrence
         __syncwarp();
         // ---- recurrence: this lane's chunk is row `lane` -------------------------------------------
         if (run) {

@@ -19,7 +19,6 @@
 namespace ssfe {
 
 constexpr int kMtN = 624, kMtM = 397;
-constexpr int kMtThreads = 512;
 
 struct RandJob {
     uint32_t seed;
@@ -49,6 +48,7 @@ __device__ __forceinline__ void bar_arrive(int id, int count)
 }
 
 constexpr int kMtRing = 4;                       // state blocks in flight between the two warp groups
+constexpr int kMtStreams = 1;                    // speaker streams advanced together by one CTA (see below)
 constexpr int kMtProd = 256, kMtCons = 256;
 constexpr int kBarFull = 1, kBarEmpty = 1 + kMtRing, kBarProd = 1 + 2 * kMtRing;
 
@@ -60,49 +60,68 @@ constexpr int kBarFull = 1, kBarEmpty = 1 + kMtRing, kBarProd = 1 + 2 * kMtRing;
 // Measured on B200: ~300 ns per 624-word block and stream whichever way the hand-off is built
 // (one group + __syncthreads 340 ns, this version 306 ns, mbarrier hand-off 360-380 ns): the floor is
 // the shared-memory round trip plus one CTA-level barrier per block, so a 400-utterance speaker
-// (61.5 k blocks) costs ~20 ms.  It runs on a side stream and is hidden behind the other stages.
-__global__ void __launch_bounds__(kMtProd + kMtCons) mt19937_kernel(const RandJob *__restrict__ jobs,
+// (61.5 k blocks) costs ~18 ms.  Advancing several streams per CTA (kMtStreams > 1) was measured
+// too: the time per round grows in proportion (1110 ns for 4 streams), i.e. the CTA is bound by its
+// own instruction issue (~900 warp instructions per block), not by barrier latency - hence few warps
+// with several words per thread here.
+__global__ void __launch_bounds__(kMtProd + kMtCons) mt19937_kernel(const RandJob *__restrict__ jobs, int n_jobs,
                                                                     const RandReq *__restrict__ reqs,
                                                                     uint2 *__restrict__ out)
 {
-    __shared__ __align__(16) uint32_t s_mt[kMtRing][kMtN];
-    const RandJob job = jobs[blockIdx.x];
-    const RandReq *rq = reqs + job.first_req;
+    extern __shared__ __align__(16) uint32_t s_mt_raw[];          // [kMtStreams][kMtRing][kMtN]
+    auto mt = [&](int s, int slot) -> uint32_t * { return s_mt_raw + (s * kMtRing + slot) * kMtN; };
     const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * kMtStreams;
+    const int ns = min(kMtStreams, n_jobs - j0);
 
-    if (tid == 0) {   // init_genrand(seed): a 624-step serial LCG, once per stream
-        uint32_t v = job.seed;
-        s_mt[0][0] = v;
+    long long nb[kMtStreams];                                      // data blocks 1..nb[s] of stream s
+    long long n_blocks = 0;
+#pragma unroll
+    for (int s = 0; s < kMtStreams; ++s) {
+        nb[s] = 0;
+        if (s < ns) {
+            const RandJob job = jobs[j0 + s];
+            const RandReq last = reqs[job.first_req + job.n_req - 1];
+            nb[s] = static_cast<long long>((last.skip + static_cast<uint64_t>(last.count) + 311) / 312);
+            n_blocks = max(n_blocks, nb[s]);
+        }
+    }
+    if (tid < ns) {   // init_genrand(seed): a 624-step serial LCG, once per stream
+        uint32_t v = jobs[j0 + tid].seed;
+        uint32_t *m0 = mt(tid, 0);
+        m0[0] = v;
         for (int i = 1; i < kMtN; ++i) {
             v = 1812433253u * (v ^ (v >> 30)) + static_cast<uint32_t>(i);
-            s_mt[0][i] = v;
+            m0[i] = v;
         }
     }
     __syncthreads();
 
-    const uint64_t last_double = rq[job.n_req - 1].skip + static_cast<uint64_t>(rq[job.n_req - 1].count);
-    const long long n_blocks = static_cast<long long>((last_double + 311) / 312);   // data blocks 1..n_blocks
-
     if (tid < kMtProd) {
         // ---- twist group --------------------------------------------------------------------------
         for (long long B = 1; B <= n_blocks; ++B) {
-            const int slot = static_cast<int>(B & (kMtRing - 1));
-            const uint32_t *o = s_mt[(B - 1) & (kMtRing - 1)];
-            uint32_t *nw = s_mt[slot];
+            const int slot = static_cast<int>(B & (kMtRing - 1)), prev = static_cast<int>((B - 1) & (kMtRing - 1));
             // slot held data block B - kMtRing: wait until the emit group is done with it
             if (B >= kMtRing + 1) bar_sync(kBarEmpty + slot, kMtProd + kMtCons);
             // Word k of the new block needs the NEW word k-227 and 3 * 227 > 624: thread t produces
             // words t, t+227, t+454 from the old block and its own results - no barrier in between.
-            if (tid < 227) {
-                const uint32_t n0 = o[tid + kMtM] ^ mt_mix(o[tid], o[tid + 1]);
-                const uint32_t n1 = n0 ^ mt_mix(o[tid + 227], o[tid + 228]);
-                nw[tid] = n0;
-                nw[tid + 227] = n1;
-                if (tid < 169) {
-                    nw[tid + 454] = n1 ^ mt_mix(o[tid + 454], o[tid + 455]);
-                } else if (tid == 169) {   // word 623 wraps around to the new word 0 (recomputed here)
-                    const uint32_t new0 = o[kMtM] ^ mt_mix(o[0], o[1]);
-                    nw[623] = n1 ^ mt_mix(o[623], new0);
+#pragma unroll
+            for (int s = 0; s < kMtStreams; ++s) {
+                if (B > nb[s]) continue;
+                const uint32_t *o = mt(s, prev);
+                uint32_t *nw = mt(s, slot);
+#pragma unroll
+                for (int t = tid; t < 227; t += kMtProd) {
+                    const uint32_t n0 = o[t + kMtM] ^ mt_mix(o[t], o[t + 1]);
+                    const uint32_t n1 = n0 ^ mt_mix(o[t + 227], o[t + 228]);
+                    nw[t] = n0;
+                    nw[t + 227] = n1;
+                    if (t < 169) {
+                        nw[t + 454] = n1 ^ mt_mix(o[t + 454], o[t + 455]);
+                    } else if (t == 169) {   // word 623 wraps around to the new word 0 (recomputed here)
+                        const uint32_t new0 = o[kMtM] ^ mt_mix(o[0], o[1]);
+                        nw[623] = n1 ^ mt_mix(o[623], new0);
+                    }
                 }
             }
             // block B complete for the twist group (the barrier also drains the shared-memory stores),
@@ -113,41 +132,57 @@ __global__ void __launch_bounds__(kMtProd + kMtCons) mt19937_kernel(const RandJo
     } else {
         // ---- emit group ---------------------------------------------------------------------------
         const int ct = tid - kMtProd;
-        int r0 = 0;
-        uint64_t r_beg = rq[0].skip, r_end = rq[0].skip + static_cast<uint64_t>(rq[0].count);
-        int64_t r_out = rq[0].out_off;
+        int r0[kMtStreams], nreq[kMtStreams];
+        uint64_t r_beg[kMtStreams], r_end[kMtStreams];
+        int64_t r_out[kMtStreams];
+        const RandReq *rq[kMtStreams];
+#pragma unroll
+        for (int s = 0; s < kMtStreams; ++s) {
+            r0[s] = 0; nreq[s] = 0; r_beg[s] = 0; r_end[s] = 0; r_out[s] = 0; rq[s] = reqs;
+            if (s < ns) {
+                const RandJob job = jobs[j0 + s];
+                rq[s] = reqs + job.first_req;
+                nreq[s] = job.n_req;
+                r_beg[s] = rq[s][0].skip;
+                r_end[s] = r_beg[s] + static_cast<uint64_t>(rq[s][0].count);
+                r_out[s] = rq[s][0].out_off;
+            }
+        }
         for (long long B = 1; B <= n_blocks; ++B) {
             const int slot = static_cast<int>(B & (kMtRing - 1));
             bar_sync(kBarFull + slot, kMtProd + kMtCons);
-            const uint32_t *nw = s_mt[slot];
             const uint64_t d0 = static_cast<uint64_t>(B - 1) * 312;   // first double of this block
-            while (r0 < job.n_req && r_end <= d0) {
-                ++r0;
-                if (r0 < job.n_req) {
-                    r_beg = rq[r0].skip;
-                    r_end = r_beg + static_cast<uint64_t>(rq[r0].count);
-                    r_out = rq[r0].out_off;
+#pragma unroll
+            for (int s = 0; s < kMtStreams; ++s) {
+                if (B > nb[s]) continue;
+                const uint32_t *nw = mt(s, slot);
+                while (r0[s] < nreq[s] && r_end[s] <= d0) {
+                    ++r0[s];
+                    if (r0[s] < nreq[s]) {
+                        r_beg[s] = rq[s][r0[s]].skip;
+                        r_end[s] = r_beg[s] + static_cast<uint64_t>(rq[s][r0[s]].count);
+                        r_out[s] = rq[s][r0[s]].out_off;
+                    }
                 }
-            }
-            if (r0 < job.n_req) {
+                if (r0[s] >= nreq[s]) continue;
                 for (int t = ct; t < 312; t += kMtCons) {
-                    if (r_beg <= d0 && d0 + 312 <= r_end) {
+                    if (r_beg[s] <= d0 && d0 + 312 <= r_end[s]) {
                         // common case: the whole block belongs to the current request
-                        out[r_out + static_cast<int64_t>(d0 - r_beg) + t] = *reinterpret_cast<const uint2 *>(nw + 2 * t);
-                    } else if (r_beg < d0 + 312) {
+                        out[r_out[s] + static_cast<int64_t>(d0 - r_beg[s]) + t] = *reinterpret_cast<const uint2 *>(nw + 2 * t);
+                    } else if (r_beg[s] < d0 + 312) {
                         const uint64_t d = d0 + t;
-                        uint64_t b = r_beg, e = r_end;
-                        int64_t oo = r_out;
-                        int r = r0;
-                        while (r < job.n_req && e <= d) {      // the block spans a request boundary
+                        uint64_t b = r_beg[s], e = r_end[s];
+                        int64_t oo = r_out[s];
+                        int r = r0[s];
+                        while (r < nreq[s] && e <= d) {      // the block spans a request boundary
                             ++r;
-                            if (r < job.n_req) {
-                                b = rq[r].skip;
-                                e = b + static_cast<uint64_t>(rq[r].count);
-                                oo = rq[r].out_off;
+                            if (r < nreq[s]) {
+                                b = rq[s][r].skip;
+                                e = b + static_cast<uint64_t>(rq[s][r].count);
+                                oo = rq[s][r].out_off;
                             }
                         }
-                        if (r < job.n_req && d >= b)
+                        if (r < nreq[s] && d >= b)
                             out[oo + static_cast<int64_t>(d - b)] = *reinterpret_cast<const uint2 *>(nw + 2 * t);
                     }
                 }
@@ -157,6 +192,8 @@ __global__ void __launch_bounds__(kMtProd + kMtCons) mt19937_kernel(const RandJo
         }
     }
 }
+
+constexpr size_t kMtSmem = static_cast<size_t>(kMtStreams) * kMtRing * kMtN * sizeof(uint32_t);
 
 __global__ void mt_convert_kernel(double *__restrict__ u, int64_t count)
 {
@@ -204,13 +241,23 @@ int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const i
         jobs.back().n_req++;
     }
     if (jobs.empty()) return SSFE_OK;
+    // streams that share a CTA should have similar lengths: order the jobs by their last position
+    std::stable_sort(jobs.begin(), jobs.end(), [&](const RandJob &a, const RandJob &b) {
+        const RandReq &ra = reqs[a.first_req + a.n_req - 1], &rb = reqs[b.first_req + b.n_req - 1];
+        return ra.skip + static_cast<uint64_t>(ra.count) > rb.skip + static_cast<uint64_t>(rb.count);
+    });
+    if (!ctx->mt_attr_set) {
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(mt19937_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(kMtSmem)));
+        ctx->mt_attr_set = true;
+    }
     if (launch_on == nullptr || launch_on == ctx->stream) {
         // public ssfe_rand path: everything on the caller's stream, doubles out
         RandJob *d_jobs = upload(ctx, jobs.data(), jobs.size());
         RandReq *d_reqs = upload(ctx, reqs.data(), reqs.size());
         if (!d_jobs || !d_reqs) return SSFE_ERR_NOMEM;
-        mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, ctx->stream>>>(
-            d_jobs, d_reqs, reinterpret_cast<uint2 *>(u_dev));
+        mt19937_kernel<<<static_cast<unsigned>((jobs.size() + kMtStreams - 1) / kMtStreams), kMtProd + kMtCons, kMtSmem, ctx->stream>>>(
+            d_jobs, static_cast<int>(jobs.size()), d_reqs, reinterpret_cast<uint2 *>(u_dev));
         SSFE_LAUNCHED(ctx);
         const int64_t total = out_off[n];
         mt_convert_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(u_dev, total);
@@ -238,11 +285,12 @@ int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const i
     memcpy(h, jobs.data(), jb);
     memcpy(h + (jb + 255) / 256 * 256, reqs.data(), rb);
     SSFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_dith_free, 0));
+    SSFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_mt_go, 0));     // see rapt_run: start beside the Viterbi kernel
     SSFE_CUDA(ctx, cudaMemcpyAsync(d, h, need, cudaMemcpyHostToDevice, st));
     mark_aux(ctx, 0, st);
-    mt19937_kernel<<<static_cast<unsigned>(jobs.size()), kMtThreads, 0, st>>>(
-        reinterpret_cast<const RandJob *>(d), reinterpret_cast<const RandReq *>(d + (jb + 255) / 256 * 256),
-        reinterpret_cast<uint2 *>(u_dev));
+    mt19937_kernel<<<static_cast<unsigned>((jobs.size() + kMtStreams - 1) / kMtStreams), kMtProd + kMtCons, kMtSmem, st>>>(
+        reinterpret_cast<const RandJob *>(d), static_cast<int>(jobs.size()),
+        reinterpret_cast<const RandReq *>(d + (jb + 255) / 256 * 256), reinterpret_cast<uint2 *>(u_dev));
     SSFE_LAUNCHED(ctx);
     mark_aux(ctx, 1, st);
     SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_join, st));

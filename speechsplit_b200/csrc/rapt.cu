@@ -995,6 +995,10 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         mark(ctx, ST_RAPT_STAT);
     }
     mark(ctx, ST_RAPT_DP);
+    // From here on the stream only runs latency- and memory-bound kernels (Viterbi, F0 post, then the
+    // next call's filtfilt passes): the place where the next call's dither walk, which needs issue
+    // slots on ~100 SMs for ~20 ms, costs the least.
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
     rapt_dp_kernel<<<static_cast<unsigned>((n + kDpWarps - 1) / kDpWarps), kDpWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     return SSFE_OK;
