@@ -122,16 +122,36 @@ __global__ void quantize_kernel(const T *__restrict__ x, int64_t count, int num_
     bins32[t] = static_cast<int>(b);
 }
 
-// one-hot rows: out[t][c] = (c == bin[t]); float4 stores where the row start allows it
+// one-hot rows: out[t][c] = (c == bin[t]).  The output is one flat stream of count * width floats
+// (width = 257 is odd, so rows are not 16-byte aligned): every thread writes one aligned float4 of that
+// stream, whose four elements may straddle two rows.
 template <typename B>
 __global__ void onehot_kernel(const B *__restrict__ bins, int64_t count, int width, float *__restrict__ out)
 {
     const int64_t total = count * width;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t t = i / width;
-        const int c = static_cast<int>(i - t * width);
-        out[i] = (static_cast<int>(bins[t]) == c) ? 1.0f : 0.0f;
+    const int64_t n4 = (total + 3) / 4;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n4;
+         q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t i = 4 * q;
+        int64_t t = i / width;
+        int c = static_cast<int>(i - t * width);
+        int b = static_cast<int>(bins[t]);
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = (c == b) ? 1.0f : 0.0f;
+            if (++c == width) {
+                c = 0;
+                ++t;
+                b = (t < count) ? static_cast<int>(bins[t]) : -1;
+            }
+        }
+        if (aligned && i + 3 < total) {
+            *reinterpret_cast<float4 *>(out + i) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int k = 0; k < 4 && i + k < total; ++k) out[i + k] = v[k];
+        }
     }
 }
 
@@ -180,7 +200,7 @@ int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_hos
         f0_dev, d_off, n, stats, total, f0_norm_dev, use_bins);
     SSFE_LAUNCHED(ctx);
     if (onehot) {
-        const int64_t work = total * 257;
+        const int64_t work = (total * 257 + 3) / 4;
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>(grid_for(work, 256), 148LL * 64));
         onehot_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(use_bins, total, 257, onehot);
         SSFE_LAUNCHED(ctx);
@@ -247,7 +267,7 @@ extern "C" int ssfe_quantize_f0(ssfe_ctx *ctx, const void *x_dev, int dtype, int
         if (h) return set_error(ctx, SSFE_ERR_RANGE, "quantize_f0: value outside [0, 1] (utils.py:52)");
     }
     if (onehot_dev) {
-        const int64_t work = count * (num_bins + 1);
+        const int64_t work = (count * (num_bins + 1) + 3) / 4;
         const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(grid_for(work, 256), 148LL * 64));
         onehot_kernel<int><<<g2, 256, 0, ctx->stream>>>(bins32, count, num_bins + 1, onehot_dev);
         SSFE_LAUNCHED(ctx);

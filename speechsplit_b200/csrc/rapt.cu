@@ -196,7 +196,9 @@ __device__ __forceinline__ int prune_candidates(float *peaks, int *locs, int nca
 // ---- K2 ------------------------------------------------------------------------------------
 constexpr int kCandWarps = 4;
 
-__global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p)
+constexpr int kCandTile = 16;      // frames per CTA (one binary search per tile, 4 frames per warp)
+
+__global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off)
 {
     __shared__ float s_db[kCandWarps][448];
     __shared__ float s_cc[kCandWarps][kCcMax];
@@ -205,16 +207,22 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
     __shared__ int s_lc[kCandWarps][kPkMax];
     __shared__ int s_st[kCandWarps][kCMax];
 
+    __shared__ double s_sq[kCandWarps][64];      // squares of the coarse window, as doubles
+    __shared__ double s_ec[kCandWarps][40];      // lagged energy per coarse lag
+
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long gf = blockIdx.x * static_cast<long long>(kCandWarps) + w;
-    if (gf >= p.total_fr) return;
     float *db = s_db[w], *cc = s_cc[w], *val = s_val[w], *pk = s_pk[w];
     int *lc = s_lc[w], *stc = s_st[w];
+    double *sq = s_sq[w], *ec = s_ec[w];
 
-    const int u = find_segment(p.fr_offs, p.n, gf);
+    const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));
     const RaptUtt ut = p.utts[u];
     const RaptCfg &cf = c_rapt.cfg[ut.cfg];
-    const int g = static_cast<int>(gf - ut.fr_off);
+    const int g_tile = (static_cast<int>(blockIdx.x) - tile_off[u]) * kCandTile;
+  for (int fk = w; fk < kCandTile; fk += kCandWarps) {
+    const int g = g_tile + fk;
+    if (g >= ut.n_fr) break;
+    const long long gf = ut.fr_off + g;
     int r, i, nfr_r;
     const int full = ut.R_last * cf.F;
     if (g < full) { r = g / cf.F; i = g - r * cf.F; nfr_r = cf.F; }
@@ -273,19 +281,23 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
                 for (int j = 0; j < size; ++j) dot0 += db[j] * db[lane + start + j];
             if (lane + 32 < nlags)
                 for (int j = 0; j < size; ++j) dot1 += db[j] * db[lane + 32 + start + j];
-            // the lagged energy is a running (sequential, double) update; every lane walks the chain
-            // but only keeps the values of its own lags - the square root and the division, the
-            // expensive part, are then done once per lag instead of once per step
-            double e0 = engc, e1 = engc;
-            for (int k = 0; k < nlags; ++k) {
-                if (k == lane) e0 = engc;
-                if (k == lane + 32) e1 = engc;
-                const float a0 = db[k + start], az = db[k + start + size];
-                engc -= static_cast<double>(a0 * a0);
-                if ((engc += static_cast<double>(az * az)) < 1.0) engc = 1.0;
+            // The lagged energy is a running (sequential, double) update.  The squares it adds and
+            // removes are formed once, in parallel (float product, then widened - as the original
+            // does); the chain itself is two double adds and a clamp per lag, and its values are
+            // published through shared memory so that the square root and the division - the
+            // expensive part - are done once per lag, by the lane that owns it.
+            for (int t = lane; t < cf.n_el; t += 32) sq[t] = static_cast<double>(db[t] * db[t]);
+            __syncwarp();
+            if (lane == 0) {
+                for (int k = 0; k < nlags; ++k) {
+                    ec[k] = engc;
+                    engc -= sq[k + start];
+                    if ((engc += sq[k + start + size]) < 1.0) engc = 1.0;
+                }
             }
-            if (lane < nlags) t0 = dot0 / sqrt(e0 * engr);
-            if (lane + 32 < nlags) t1 = dot1 / sqrt(e1 * engr);
+            __syncwarp();
+            if (lane < nlags) t0 = dot0 / sqrt(ec[lane] * engr);
+            if (lane + 32 < nlags) t1 = dot1 / sqrt(ec[lane + 32] * engr);
         }
         if (lane < nlags) cc[lane] = t0;
         if (lane + 32 < nlags) cc[lane + 32] = t1;
@@ -417,6 +429,8 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
         }
         if (lane == 0) p.ncand[gf] = static_cast<unsigned char>(ncand + 1);
     }
+    __syncwarp();
+  }   // frames of this warp
 }
 
 // ---- K3 ------------------------------------------------------------------------------------
@@ -931,13 +945,16 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     }
     fr_offs[n] = fr;
     ds_offs[n] = dsn;
-    std::vector<int> stat_tile_off(n + 1);
-    long long stat_tiles = 0;
+    std::vector<int> stat_tile_off(n + 1), cand_tile_off(n + 1);
+    long long stat_tiles = 0, cand_tiles = 0;
     for (int i = 0; i < n; ++i) {
         stat_tile_off[i] = static_cast<int>(stat_tiles);
+        cand_tile_off[i] = static_cast<int>(cand_tiles);
         stat_tiles += (utts[i].n_fr + kStatFrames - 1) / kStatFrames;
+        cand_tiles += (utts[i].n_fr + kCandTile - 1) / kCandTile;
     }
     stat_tile_off[n] = static_cast<int>(stat_tiles);
+    cand_tile_off[n] = static_cast<int>(cand_tiles);
 
     int rc;
     if ((rc = ensure(ctx, ctx->ws.rapt_ds, dsn * sizeof(float)))) return rc;
@@ -948,7 +965,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     memset(&p, 0, sizeof(p));
     p.wav = wav_base;
     const int *d_stat_tiles = upload(ctx, stat_tile_off.data(), n + 1);
-    if (!d_stat_tiles) return SSFE_ERR_NOMEM;
+    const int *d_cand_tiles = upload(ctx, cand_tile_off.data(), n + 1);
+    if (!d_stat_tiles || !d_cand_tiles) return SSFE_ERR_NOMEM;
     p.utts = upload(ctx, utts.data(), n);
     p.fr_offs = upload(ctx, fr_offs.data(), n + 1);
     p.ds_offs = upload(ctx, ds_offs.data(), n + 1);
@@ -986,7 +1004,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     SSFE_LAUNCHED(ctx);
     mark(ctx, ST_RAPT_CAND);
     if (fr > 0) {
-        rapt_cand_kernel<<<static_cast<unsigned>((fr + kCandWarps - 1) / kCandWarps), kCandWarps * 32, 0, st>>>(p);
+        rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles);
         SSFE_LAUNCHED(ctx);
         mark(ctx, ST_RAPT_STAT);
         rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles);
