@@ -111,6 +111,18 @@ int ssfe_filtfilt(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *sa
 int ssfe_rand(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_offsets,
               int n_utts, double *u_dev);
 
+/* Host-only helpers behind ssfe_rand (no GPU needed; exported so that the algebra can be tested on
+ * the CPU against numpy).  MT19937 is linear over GF(2): with phi its characteristic polynomial
+ * (degree 19937) and g = x^J mod phi, the untempered word sequence obeys w[n+J] = XOR_{g_i=1} w[n+i],
+ * which is how the GPU starts a speaker's stream (make_spect_f0.py:47,55) in many places at once.
+ *   ssfe_mt_charpoly_terms: number of terms of phi below x^19937 (exponents into exps, up to cap)
+ *   ssfe_mt_jump_poly:      x^n_words mod phi as 312 little-endian 64-bit words; 0 on success
+ *   ssfe_mt_jump_taps:      exponents of x^(d * 256^level * unit_words) mod phi, ascending; returns
+ *                           their number (d = 1..255, level = 0..2), or -1 */
+int ssfe_mt_charpoly_terms(int *exps, int cap);
+int ssfe_mt_jump_poly(uint64_t n_words, uint64_t *poly312);
+int ssfe_mt_jump_taps(uint64_t unit_words, int level, int d, uint16_t *taps, int cap);
+
 /* (a3) utils.pySTFT(x) (utils.py:18-31) for 1-D inputs: reflect-pad 512, hop 256, periodic
  * Hann(1024), |rfft|.  wav_dev float32 concatenated, offsets host [n+1] (lengths as given, no
  * fix-up).  mag_dev: float32 [total_frames, 513] (frame-major, i.e. the transpose of pySTFT's

@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libssfe.so")
 OBJ = os.path.join(PKG, "_obj")
 CU = ["api.cu", "stft_mel.cu", "filtfilt.cu", "mt19937.cu", "f0_post.cu", "rapt.cu"]
-CPP = ["filt_consts.cpp"]
+CPP = ["filt_consts.cpp", "mt_jump.cpp"]
 # RAPT reproduces the original's float evaluation order; fused multiply-adds would change it
 EXTRA = {"rapt.cu": ["--fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

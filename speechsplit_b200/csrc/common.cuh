@@ -29,6 +29,7 @@ struct Workspace {
     DevBuf wavp, y1, dith, meta_dev, tiles, misc;
     DevBuf rapt_ds, rapt_cand, rapt_stat, rapt_f0;
     DevBuf carry;
+    DevBuf mt_state, mt_state_aux;     // segment start states of the dither streams (mt19937.cu)
 };
 
 struct MelTables {
@@ -58,6 +59,11 @@ struct ssfe_ctx {
     cudaEvent_t aux_free[2] = {nullptr, nullptr};
     int aux_idx = 0;
     bool mt_attr_set = false;
+    // MT19937 jump-ahead tap lists (mt19937.cu): slot + 1 per (level, digit), 0 = not built yet
+    int mt_slot[3][256] = {};
+    int mt_cnt[3][256] = {};
+    uint16_t *mt_taps = nullptr;
+    int mt_slots_used = 0, mt_slots_cap = 0;
     ssfe_config cfg;
     std::vector<float> mel_basis;      // host copy (513 x 80)
     char err[512];

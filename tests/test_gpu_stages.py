@@ -60,6 +60,44 @@ def test_rand_block_boundaries(fe):
         assert np.array_equal(u.cpu().numpy(), ref[skip:skip + cnt])
 
 
+def _stream_slice(seed, skip, cnt):
+    rs = RandomState(seed)
+    left = skip
+    while left > 0:
+        step = min(left, 20_000_000)
+        rs.rand(step)
+        left -= step
+    return rs.rand(cnt)
+
+
+def test_rand_segment_jumps(fe):
+    """The generator cuts every stream into segments of 4096 state blocks (1 277 952 doubles) and
+    jumps to their start states (mt19937.cu / mt_jump.cpp): requests that cross segment edges, start
+    deep inside a stream, share a segment, or leave whole segments untouched must still be the
+    bits numpy produces."""
+    seg = 4096 * 312
+    ref = RandomState(226).rand(3 * seg + 5000)
+    cases = [(seg - 1000, 5000), (seg, 312), (2 * seg - 1, 2), (0, 2 * seg + 17), (3 * seg - 7, 3000)]
+    for skip, cnt in cases:
+        u, _ = fe.rand([226], [skip], [cnt])
+        assert np.array_equal(u.cpu().numpy(), ref[skip:skip + cnt]), (skip, cnt)
+    # several requests of one stream in one call, with a gap of more than a segment between them
+    skips = [100, seg - 50, 2 * seg + 999, 3 * seg + 100]
+    counts = [seg - 200, 100, 40000, 4000]
+    u, off = fe.rand([226] * 4, skips, counts)
+    u = u.cpu().numpy()
+    for k in range(4):
+        assert np.array_equal(u[off[k]:off[k + 1]], ref[skips[k]:skips[k] + counts[k]]), k
+
+
+def test_rand_deep_stream_positions(fe):
+    """Segment indices above 255 need two jump polynomials (base-256 digits)."""
+    seg = 4096 * 312
+    for seed, skip, cnt in ((300, 17 * seg + 12345, 70000), (9, 257 * seg - 4000, 10000)):
+        u, _ = fe.rand([seed], [skip], [cnt])
+        assert np.array_equal(u.cpu().numpy(), _stream_slice(seed, skip, cnt)), (seed, skip)
+
+
 # ---- a0 + a1: filtfilt -------------------------------------------------------------------------
 def _filtfilt_cases():
     rng = np.random.default_rng(11)
