@@ -43,6 +43,27 @@ int ensure(ssfe_ctx *ctx, DevBuf &b, size_t bytes)
     return SSFE_OK;
 }
 
+// Metadata goes from the pinned arena to the device arena with a tiny KERNEL that reads the pinned
+// pages over PCIe (UVA), not with cudaMemcpyAsync: a copy-engine transfer queues behind whatever the
+// engine is already doing, and in ssfe_extract_host that is a 0.5 GB PCM upload - every stage of the
+// sub-batch being computed then waited ~9 ms for its few hundred bytes of offsets (measured: 25.8 ms
+// per sub-batch instead of 16.4).
+__global__ void meta_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+}
+
+int stage_copy(ssfe_ctx *ctx, void *dst_dev, const void *src_pinned, size_t bytes, cudaStream_t st)
+{
+    const size_t n16 = (bytes + 15) / 16;
+    if (n16 == 0) return SSFE_OK;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n16 + 255) / 256, 4 * static_cast<size_t>(ctx->num_sms)));
+    meta_copy_kernel<<<grid, 256, 0, st>>>(static_cast<uint4 *>(dst_dev), static_cast<const uint4 *>(src_pinned), n16);
+    return cudaGetLastError() == cudaSuccess ? SSFE_OK : SSFE_ERR_CUDA;
+}
+
 void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
 {
     const size_t need = (bytes + 255) / 256 * 256;
@@ -70,7 +91,7 @@ void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
     char *h = ctx->meta_host + ctx->meta_used;
     char *d = ctx->meta_dev + ctx->meta_used;
     memcpy(h, host, bytes);
-    if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    if (stage_copy(ctx, d, h, bytes, ctx->stream) != SSFE_OK) {
         set_error(ctx, SSFE_ERR_CUDA, "metadata upload failed");
         return nullptr;
     }
@@ -240,6 +261,10 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (ssfe_ctx *&ln : ctx->lane) {
+        ssfe_destroy(ln);
+        ln = nullptr;
+    }
     free_stft_tables(ctx);
     free_filtfilt(ctx);
     free_rapt(ctx);
@@ -257,7 +282,8 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
             if (e) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1], ctx->ev_h2d[0],
-                          ctx->ev_h2d[1], ctx->ev_comp[0], ctx->ev_comp[1], ctx->ev_d2h[0], ctx->ev_d2h[1]})
+                          ctx->ev_h2d[1], ctx->ev_h2d[2], ctx->ev_h2d[3], ctx->ev_comp[0], ctx->ev_comp[1], ctx->ev_comp[2], ctx->ev_comp[3],
+                          ctx->ev_d2h[0], ctx->ev_d2h[1], ctx->ev_d2h[2], ctx->ev_d2h[3]})
         if (e) cudaEventDestroy(e);
     for (auto &row : ctx->ev_auxr)
         for (cudaEvent_t e : row)
@@ -448,11 +474,11 @@ extern "C" int ssfe_extract(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_de
     return extract_device(ctx, b, x_dev, dtype, o, fix, foff);
 }
 
-// Host buffers in and out.  The batch is cut into sub-batches of ~64 M samples that flow through three
-// streams - H2D of sub-batch c+1, the kernels of sub-batch c and D2H of sub-batch c-1 overlap (input
-// and output slots are double buffered).  The dither streams of ALL sub-batches are generated once,
-// up front, on the side stream: a speaker's MT19937 stream is sequential, so regenerating it per
-// sub-batch would repeat the walk from the seed every time.
+// Host buffers in and out.  The batch is cut into sub-batches (host_chunk_samples, 256 M samples by
+// default, ramping up at the start and down at the end) that flow through the PCM upload stream, two
+// compute lanes and the download stream: H2D of later sub-batches, the kernels of two sub-batches and
+// D2H of an earlier one overlap; input and output slots are four deep.  Every lane generates the
+// dither of its own sub-batches (jump-ahead makes any stream position cheap, mt19937.cu).
 extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_host, int dtype, float *mel_host,
                                  float *f0_norm_host, int64_t *bins_host)
 {
@@ -467,15 +493,44 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     std::vector<int64_t> fix(n + 1), foff(n + 1);
     ssfe_plan_offsets(b->sample_offsets, n, fix.data(), foff.data());
 
-    // sub-batches: cut at ~kChunkSamples, preferably where the speaker changes
+    // Sub-batches of ~kChunkSamples, cut preferably where the speaker changes.  The first upload and the
+    // last download are not hidden behind anything, so the schedule ramps up (1/4, 1/2, 1, 1, ...) and
+    // down again (..., 1/2, 1/4).
     const int64_t kChunkSamples = ctx->host_chunk_samples;
+    std::vector<int64_t> targets;
+    {
+        int64_t remaining = b->sample_offsets[n] - b->sample_offsets[0];
+        const int64_t q = std::max<int64_t>(kChunkSamples / 4, 1), tail_sum = 3 * q;
+        const bool ramp = !getenv("SSFE_HOST_NORAMP");
+        for (int64_t h : {q, 2 * q})
+            if (ramp && remaining > tail_sum + h) {
+                targets.push_back(h);
+                remaining -= h;
+            }
+        while (remaining > tail_sum + kChunkSamples) {
+            targets.push_back(kChunkSamples);
+            remaining -= kChunkSamples;
+        }
+        if (ramp && remaining > tail_sum) {
+            targets.push_back(remaining - tail_sum);
+            remaining = tail_sum;
+        }
+        if (ramp && remaining > q) {
+            targets.push_back(remaining - q);
+            remaining = q;
+        }
+        targets.push_back(remaining);
+    }
     std::vector<int> cuts{0};
     {
         int start = 0;
+        size_t ti = 0;
         while (start < n) {
+            const int64_t want = targets[std::min(ti, targets.size() - 1)];
+            ++ti;
             int end = start;
             int64_t acc = 0;
-            while (end < n && (acc < kChunkSamples || end == start)) {
+            while (end < n && (acc < want || end == start)) {
                 acc += b->sample_offsets[end + 1] - b->sample_offsets[end];
                 ++end;
             }
@@ -493,28 +548,45 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         max_in = std::max(max_in, b->sample_offsets[cuts[c + 1]] - b->sample_offsets[cuts[c]]);
         max_fr = std::max(max_fr, foff[cuts[c + 1]] - foff[cuts[c]]);
     }
-    // double-buffered device slots: [x | mel | f0 | bins]
+    // Two compute lanes (full contexts of their own: stream, side stream, workspace) take the
+    // sub-batches alternately, so that the serial chains inside a sub-batch (filter carries, Viterbi,
+    // the tails of 20 kernels) are covered by the other lane's kernels instead of idling the GPU.
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->lane[i]) {
+            if ((rc = ssfe_create(&ctx->lane[i], ctx->device, &ctx->cfg)))
+                return set_error(ctx, rc, "ssfe_extract_host: lane context: %s", ssfe_last_error(nullptr));
+        }
+    // device slots [x | mel | f0 | bins], kHostSlots deep so that uploads run ahead of both lanes
+    constexpr int kS = ssfe_ctx::kHostSlots;
     const size_t in_b = (max_in * esz + 255) / 256 * 256, mel_b = (max_fr * kMels * 4 + 255) / 256 * 256,
                  f0_b = (max_fr * 4 + 255) / 256 * 256, bins_b = bins_host ? (max_fr * 8 + 255) / 256 * 256 : 0;
     const size_t slot_b = in_b + mel_b + f0_b + bins_b;
-    if ((rc = ensure(ctx, ctx->h_x, 2 * slot_b))) return rc;
-    if ((rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
-    for (int i = 0; i < 2; ++i)
+    const int n_slots = std::min(kS, n_chunks);
+    if ((rc = ensure(ctx, ctx->h_x, n_slots * slot_b))) return rc;
+    for (int i = 0; i < kS; ++i)
         for (cudaEvent_t *e : {&ctx->ev_h2d[i], &ctx->ev_comp[i], &ctx->ev_d2h[i]})
             if (!*e) SSFE_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 
-    // all dither streams, once, on the side stream
-    double *dith = static_cast<double *>(ctx->ws.dith.p);
-    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
-
-    // the copy streams must not run ahead of work already queued on the compute stream
+    // nothing here may run ahead of work already queued on the caller's stream
     SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
     SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_fork, 0));
+    for (int i = 0; i < 2; ++i) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[i]->stream, ctx->ev_fork, 0));
 
+    const bool trace = getenv("SSFE_TRACE_HOST") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto tmark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    tmark(ctx->stream);
     const char *src = static_cast<const char *>(x_host);
     for (int c = 0; c < n_chunks; ++c) {
-        const int u0 = cuts[c], u1 = cuts[c + 1], m = u1 - u0, slot = c & 1;
+        const int u0 = cuts[c], u1 = cuts[c + 1], m = u1 - u0, slot = c % n_slots;
+        ssfe_ctx *ln = ctx->lane[c & 1];
         char *base = static_cast<char *>(ctx->h_x.p) + slot * slot_b;
         void *d_x = base;
         float *d_mel = reinterpret_cast<float *>(base + in_b);
@@ -523,14 +595,15 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         const int64_t s0 = b->sample_offsets[u0], ns = b->sample_offsets[u1] - s0;
         const int64_t f0 = foff[u0], nf = foff[u1] - f0;
 
-        // H2D (slot free once the kernels of sub-batch c-2 are done with it)
-        if (c >= 2) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[slot], 0));
+        // H2D (the slot's input is free once the kernels of sub-batch c - n_slots are done with it)
+        if (c >= n_slots) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[slot], 0));
         SSFE_CUDA(ctx, cudaMemcpyAsync(d_x, src + s0 * esz, ns * esz, cudaMemcpyHostToDevice, ctx->copy_in));
         SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_in));
+        tmark(ctx->copy_in);
 
-        // kernels (outputs of sub-batch c-2 must have left the slot)
-        SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
-        if (c >= 2) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[slot], 0));
+        // kernels (the slot's outputs of sub-batch c - n_slots must have left for the host)
+        SSFE_CUDA(ctx, cudaStreamWaitEvent(ln->stream, ctx->ev_h2d[slot], 0));
+        if (c >= n_slots) SSFE_CUDA(ctx, cudaStreamWaitEvent(ln->stream, ctx->ev_d2h[slot], 0));
         std::vector<int64_t> rel(m + 1), cfix(m + 1), cfoff(m + 1);
         for (int i = 0; i <= m; ++i) {
             rel[i] = b->sample_offsets[u0 + i] - s0;
@@ -549,8 +622,12 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         o.mel = d_mel;
         o.f0_norm = d_f0;
         o.bins = d_bins;
-        if ((rc = extract_device(ctx, &cb, d_x, dtype, &o, cfix, cfoff, dith + fix[u0]))) return rc;
-        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->stream));
+        tmark(ln->stream);
+        if ((rc = extract_device(ln, &cb, d_x, dtype, &o, cfix, cfoff))) return set_error(ctx, rc, "%s", ln->err);
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ln->stream));
+        tmark(ln->stream);
+        ctx->launches += ln->launches;
+        ln->launches = 0;
 
         // D2H
         SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[slot], 0));
@@ -559,9 +636,21 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         if (bins_host)
             SSFE_CUDA(ctx, cudaMemcpyAsync(bins_host + f0, d_bins, nf * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
         SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[slot], ctx->copy_out));
+        tmark(ctx->copy_out);
     }
-    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, ctx->stream));   // the shared dither buffer may be refilled
-    SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
-    SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));      // every sub-batch's results are on the host
+    for (int i = 0; i < 2; ++i) SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->lane[i]->stream));
+    if (trace) {
+        for (int c = 0; c < n_chunks; ++c) {
+            float a, b2, cc, d;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 4 * c]);
+            cudaEventElapsedTime(&b2, tev[0], tev[2 + 4 * c]);
+            cudaEventElapsedTime(&cc, tev[0], tev[3 + 4 * c]);
+            cudaEventElapsedTime(&d, tev[0], tev[4 + 4 * c]);
+            fprintf(stderr, "[host] chunk %d utts %d: h2d done %.2f | comp %.2f -> %.2f (%.2f) | d2h done %.2f\n", c, cuts[c + 1] - cuts[c], a,
+                    b2, cc, cc - b2, d);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return SSFE_OK;
 }

@@ -51,7 +51,9 @@ struct ssfe_ctx {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // ssfe_extract_host pipeline
     cudaStream_t aux = nullptr;                               // the dither stream runs beside filtfilt
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    static constexpr int kHostSlots = 4;                      // device slots of ssfe_extract_host
+    cudaEvent_t ev_h2d[kHostSlots] = {}, ev_comp[kHostSlots] = {}, ev_d2h[kHostSlots] = {};
+    ssfe_ctx *lane[2] = {nullptr, nullptr};                   // compute lanes of ssfe_extract_host (created on first use)
     cudaEvent_t ev_dith_free = nullptr;                       // recorded after the kernel that reads `dith`
     cudaEvent_t ev_mt_go = nullptr;                           // recorded where the NEXT call's dither walk may start
     char *aux_host[2] = {nullptr, nullptr}, *aux_dev[2] = {nullptr, nullptr};   // side-stream metadata staging
@@ -105,6 +107,8 @@ int cuda_fail(ssfe_ctx *ctx, cudaError_t e, const char *what);
 int ensure(ssfe_ctx *ctx, DevBuf &b, size_t bytes);
 // copies `bytes` of host metadata to the device through the pinned arena; returns device pointer
 void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes);
+// pinned host -> device by a small kernel on `st` (keeps metadata off the copy engines, see api.cu)
+int stage_copy(ssfe_ctx *ctx, void *dst_dev, const void *src_pinned, size_t bytes, cudaStream_t st);
 template <typename T>
 inline T *upload(ssfe_ctx *ctx, const T *host, size_t n)
 {
@@ -166,9 +170,10 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
 int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
                        const int64_t *fix_off_dev, int n);
 
-// launch_on: stream for the kernel (metadata still travels on ctx->stream; ordering handled inside)
+// launch_on: nullptr / ctx->stream = public path (doubles out); ctx->aux = side stream, raw word pairs
+// out, ordering handled inside.  gate: wait for ev_mt_go (start beside the previous call's Viterbi kernel).
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
-             int n, double *u_dev, cudaStream_t launch_on = nullptr);
+             int n, double *u_dev, cudaStream_t launch_on = nullptr, bool gate = true);
 
 int init_rapt(ssfe_ctx *ctx);
 void free_rapt(ssfe_ctx *ctx);
