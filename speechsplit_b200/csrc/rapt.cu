@@ -48,6 +48,7 @@ struct RaptConsts {
     float co[kNco];
     float cand_thresh, tcost, tfact_a, tfact_s, vbias, ffact, preemp;
     float ln2, fdouble, freqwt;
+    float one;                       // 1.0f the compiler cannot see (f2add below)
     int size_frame_hist, size_frame_out;
 };
 
@@ -460,25 +461,72 @@ __device__ __forceinline__ void durbin18(const float *r, float *a_out, float *er
     *err = e;
 }
 
+// Packed FP32 (sm_100a: mul / fma.rn.f32x2 -> FMUL2 / FFMA2, one issue slot for two lanes).  This
+// file is compiled with --fmad=false because the original rounds every product before it is added;
+// the packed forms keep exactly that rounding while halving the instruction count of a multiply-add.
+// Pairs live in 64-bit registers (p2) so that they stay packed between uses.
+typedef unsigned long long p2;
+__device__ __forceinline__ p2 pk(float x, float y)
+{
+    p2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float p2lo(p2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return x;
+}
+__device__ __forceinline__ float p2hi(p2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return y;
+}
+__device__ __forceinline__ p2 p2mul(p2 a, p2 b)
+{
+    p2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a + b as fma(b, one, a) with `one` = 1.0f read from constant memory.  ptxas (12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false and explicit rounding modifiers
+// (and still does when the 1 is a literal), which would skip the rounding of the product; an fma
+// whose multiplier it cannot see is never merged with the multiply that feeds it, and b * 1 + a
+// rounds exactly like a + b.  SASS: FMUL2 + FFMA2 R, R.F32x2, UR.F32, R.F32x2.
+__device__ __forceinline__ p2 p2add(p2 a, p2 b)
+{
+    p2 r;
+    asm("{.reg .b64 ro; mov.b64 ro, {%3,%3}; fma.rn.f32x2 %0, %2, ro, %1;}" : "=l"(r) : "l"(a), "l"(b), "f"(c_rapt.one));
+    return r;
+}
+
 // One THREAD per 30 ms window.  The 19 autocorrelation chains (lags 0..18) of a window all consume
-// the same samples, so a thread keeps a sliding window of 19 pre-emphasised, Hanning-weighted samples
-// in registers and feeds 19 accumulators from it: one shared-memory read per 19 multiply-adds,
-// instead of two per multiply-add when a lane owns a single lag.  Every chain is still summed left to
-// right by one thread, so the result is bit-identical to the serial original.
+// the same samples, so a thread keeps a sliding window of pre-emphasised, Hanning-weighted samples in
+// registers and feeds the chains from it; every chain is still summed left to right by one thread,
+// product rounded before the add, so the result is bit-identical to the serial original.
+// The chains are held as PAIRS (lag 2t, lag 2t+1) and advanced with packed multiplies and adds: for
+// sample j the pair needs (d[j+2t], d[j+2t+1]), i.e. even-aligned sample pairs E for even j and
+// odd-aligned pairs O for odd j; both are rings of 11 register pairs, refilled by one packed
+// produce step (window, pre-emphasis, energy) per two samples.  20 packed + ~3 move instructions
+// per sample instead of 38 scalar ones.
 // A CTA covers 32 consecutive frames of one utterance: warp 0 takes the current windows
 // (x + 256 g - 80), warp 1 the previous ones (x + 256 g - 400); the signal span is staged once
-// in shared memory (scaled by 32768, one pad word per 256 samples -> conflict-free column reads).
+// in shared memory (scaled by 32768, two pad words per 256 samples -> conflict-free 64-bit column reads).
 constexpr int kStatFrames = 32;
 constexpr int kStatSpan = kHop * (kStatFrames - 1) + kStatGap + kStatW;      // 16928 samples
-__device__ __forceinline__ int stat_skew(int i) { return i + (i >> 8); }
+constexpr int kStatSpanPad = kStatSpan + 32;                                  // read-ahead of the last window
+constexpr int kStatXWords = kStatSpanPad + 2 * (kStatSpanPad / 256) + 2;
+constexpr int kStatWinPairs = 256;                                            // window pairs (zero past 479 / 480)
+__device__ __forceinline__ int stat_skew(int i) { return i + 2 * (i >> 8); }
 
 __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptParams p, const int *__restrict__ tile_off)
 {
-    extern __shared__ float s_stat[];
-    float *s_x = s_stat;                                   // [kStatSpan + kStatSpan/256 + 1]
-    float *s_w479 = s_x + kStatSpan + kStatSpan / 256 + 2; // [480]
-    float *s_w480 = s_w479 + kStatW;                       // [480]
-    float *s_ex = s_w480 + kStatW;                         // [frames][20]: rho1[1..18], err1, rms1 of the previous window
+    extern __shared__ __align__(16) float s_stat[];
+    float4 *s_w4 = reinterpret_cast<float4 *>(s_stat);      // [256] {w480[i], w480[i+1], w479[i], w479[i+1]}, i = 2q
+    float *s_x = s_stat + 4 * kStatWinPairs;                // [kStatXWords], skewed
+    float *s_ex = s_x + kStatXWords;                        // [frames][20]: rho1[1..18], err1, rms1 of the previous window
 
     const int tid = threadIdx.x;
     const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));
@@ -486,7 +534,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     const int g0 = (static_cast<int>(blockIdx.x) - tile_off[u]) * kStatFrames;
     const float *x = p.wav + ut.wav_off;
     const int s_lo = kHop * g0 - (kStatGap + 80);
-    for (int i0 = 0; i0 < kStatSpan; i0 += 16 * 2 * kStatFrames) {   // 16 loads in flight per thread
+    for (int i0 = 0; i0 < kStatSpanPad; i0 += 16 * 2 * kStatFrames) {   // 16 loads in flight per thread
         float raw[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -496,12 +544,17 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int i = i0 + tid + q * 2 * kStatFrames, idx = s_lo + i;
-            if (i < kStatSpan) s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+            if (i < kStatSpanPad) s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
         }
     }
-    for (int i = tid; i < kStatW; i += 2 * kStatFrames) {
-        s_w479[i] = (i < kStatW - 1) ? p.w479[i] : 0.0f;
-        s_w480[i] = p.w480[i];
+    for (int q = tid; q < kStatWinPairs; q += 2 * kStatFrames) {
+        const int i = 2 * q;
+        float4 w;
+        w.x = (i < kStatW) ? p.w480[i] : 0.0f;
+        w.y = (i + 1 < kStatW) ? p.w480[i + 1] : 0.0f;
+        w.z = (i < kStatW - 1) ? p.w479[i] : 0.0f;
+        w.w = (i + 1 < kStatW - 1) ? p.w479[i + 1] : 0.0f;
+        s_w4[q] = w;
     }
     __syncthreads();
 
@@ -514,40 +567,55 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     float acc[kLpcOrd + 1];
     float rms = 0.0f;
     if (live) {
-        float v[kLpcOrd + 1];
         float en = 0.0f;
-        float xi = s_x[stat_skew(b)];
-        // produce(i): windowed pre-emphasised sample d[i] (0 for i >= 479), energy term of sample i
-        auto produce = [&](int i) -> float {
-            float d = 0.0f;
-            if (i < kStatW) {
-                const float f = s_w480[i] * xi;
-                en += f * f;
-                if (i < kStatW - 1) {
-                    const float xn = s_x[stat_skew(b + i + 1)];
-                    d = s_w479[i] * (xn - (c_rapt.preemp * xi));
-                    xi = xn;
-                }
-            }
+        const p2 npre = pk(-c_rapt.preemp, -c_rapt.preemp);
+        auto ldx = [&](int i) -> p2 {                      // (x[b+i], x[b+i+1]), i even
+            const int a = b + i;
+            return *reinterpret_cast<const p2 *>(s_x + stat_skew(a));
+        };
+        p2 xc = ldx(0);
+        // produce2(i): the windowed pre-emphasised samples (d[i], d[i+1]) - zero from 479 on - and the
+        // energy terms of samples i, i+1 (zero from 480 on), in the original's order
+        auto produce2 = [&](int i) -> p2 {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(s_w4 + (i >> 1));   // (w480 pair, w479 pair)
+            const p2 xn = ldx(i + 2);
+            const p2 f = p2mul(w.x, xc);
+            const p2 ff = p2mul(f, f);
+            en += p2lo(ff);
+            en += p2hi(ff);
+            const p2 t = p2mul(npre, xc);                                      // -(preemp * x[i])
+            const p2 d = p2mul(w.y, p2add(pk(p2hi(xc), p2lo(xn)), t));
+            xc = xn;
             return d;
         };
+        p2 E[11], O[11], A[10];
 #pragma unroll
-        for (int k = 0; k <= kLpcOrd; ++k) {
-            v[k] = produce(k);
-            acc[k] = 0.0f;
+        for (int t = 0; t < 11; ++t) E[t] = produce2(2 * t);
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            O[t] = pk(p2hi(E[t]), p2lo(E[t + 1]));
+            A[t] = pk(0.0f, 0.0f);
         }
-        const int wsize = kStatW - 1;
-        for (int jb = 0; jb * (kLpcOrd + 1) < wsize; ++jb) {
+        O[10] = pk(0.0f, 0.0f);
+        // 22 x 11 double steps = 484 samples; the ones past 478 are zeros and add nothing
+        for (int jb = 0; jb < 22; ++jb) {
 #pragma unroll
-            for (int r = 0; r <= kLpcOrd; ++r) {
-                const int j = jb * (kLpcOrd + 1) + r;
-                if (j < wsize) {
-                    const float dj = v[r];
+            for (int st = 0; st < 11; ++st) {
+                const p2 cur = E[st];
+                const p2 d0 = pk(p2lo(cur), p2lo(cur)), d1 = pk(p2hi(cur), p2hi(cur));
 #pragma unroll
-                    for (int k = 0; k <= kLpcOrd; ++k) acc[k] += dj * v[(r + k) % (kLpcOrd + 1)];
-                    v[r] = produce(j + kLpcOrd + 1);
-                }
+                for (int t = 0; t < 10; ++t) A[t] = p2add(A[t], p2mul(d0, E[(st + t) % 11]));
+#pragma unroll
+                for (int t = 0; t < 10; ++t) A[t] = p2add(A[t], p2mul(d1, O[(st + t) % 11]));
+                const p2 nw = produce2(22 * jb + 2 * st + 22);
+                O[(st + 10) % 11] = pk(p2hi(E[(st + 10) % 11]), p2lo(nw));
+                E[st] = nw;
             }
+        }
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            acc[2 * t] = p2lo(A[t]);
+            if (2 * t + 1 <= kLpcOrd) acc[2 * t + 1] = p2hi(A[t]);
         }
         rms = static_cast<float>(sqrt(static_cast<double>(en / kStatW)));
     }
@@ -601,7 +669,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     p.sta[gf] = static_cast<float>(0.2 / t);
 }
 
-constexpr size_t kStatSmem = (kStatSpan + kStatSpan / 256 + 2 + 2 * kStatW + kStatFrames * 20) * sizeof(float);
+constexpr size_t kStatSmem = (4 * kStatWinPairs + kStatXWords + kStatFrames * 20) * sizeof(float);
 
 // ---- K4 ------------------------------------------------------------------------------------
 // The kernel is one latency chain per utterance, so every round trip to global memory inside the
@@ -803,6 +871,7 @@ int init_rapt(ssfe_ctx *ctx)
     const float ln2 = static_cast<float>(log(2.0));
     const float freqwt = freq_weight / frame_int;
     h.ln2 = ln2;
+    h.one = 1.0f;
     h.fdouble = double_cost;
     h.freqwt = freqwt;
     std::vector<double> log_lag(336, 0.0);
