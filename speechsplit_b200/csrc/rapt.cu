@@ -194,6 +194,47 @@ __device__ __forceinline__ int prune_candidates(float *peaks, int *locs, int nca
     return kCMax - 1;
 }
 
+// Packed FP32 (sm_100a: mul / fma.rn.f32x2 -> FMUL2 / FFMA2, one issue slot for two lanes).  This
+// file is compiled with --fmad=false because the original rounds every product before it is added;
+// the packed forms keep exactly that rounding while halving the instruction count of a multiply-add.
+// Pairs live in 64-bit registers (p2) so that they stay packed between uses.
+typedef unsigned long long p2;
+__device__ __forceinline__ p2 p2pack(float x, float y)
+{
+    p2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float p2lo(p2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return x;
+}
+__device__ __forceinline__ float p2hi(p2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return y;
+}
+__device__ __forceinline__ p2 p2mul(p2 a, p2 b)
+{
+    p2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a + b as fma(b, one, a) with `one` = 1.0f read from constant memory.  ptxas (12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false and explicit rounding modifiers
+// (and still does when the 1 is a literal), which would skip the rounding of the product; an fma
+// whose multiplier it cannot see is never merged with the multiply that feeds it, and b * 1 + a
+// rounds exactly like a + b.  SASS: FMUL2 + FFMA2 R, R.F32x2, UR.F32, R.F32x2.
+__device__ __forceinline__ p2 p2add(p2 a, p2 b)
+{
+    p2 r;
+    asm("{.reg .b64 ro; mov.b64 ro, {%3,%3}; fma.rn.f32x2 %0, %2, ro, %1;}" : "=l"(r) : "l"(a), "l"(b), "f"(c_rapt.one));
+    return r;
+}
+
 // ---- K2 ------------------------------------------------------------------------------------
 constexpr int kCandWarps = 4;
 
@@ -201,19 +242,20 @@ constexpr int kCandTile = 16;      // frames per CTA (one binary search per tile
 
 __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off)
 {
-    __shared__ float s_db[kCandWarps][448];
-    __shared__ float s_cc[kCandWarps][kCcMax];
+    __shared__ __align__(16) float s_db[kCandWarps][448];
+    __shared__ __align__(16) float s_cc[kCandWarps][kCcMax];        // fine stage: first the lagged energies (double[140])
     __shared__ float s_val[kCandWarps][kCMax * 7 + 4];
-    __shared__ float s_pk[kCandWarps][kPkMax];
-    __shared__ int s_lc[kCandWarps][kPkMax];
+    __shared__ __align__(16) float s_pklc[kCandWarps][2 * kPkMax];  // peaks | lags; between prune and pick: fine squares
     __shared__ int s_st[kCandWarps][kCMax];
 
     __shared__ double s_sq[kCandWarps][64];      // squares of the coarse window, as doubles
     __shared__ double s_ec[kCandWarps][40];      // lagged energy per coarse lag
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float *db = s_db[w], *cc = s_cc[w], *val = s_val[w], *pk = s_pk[w];
-    int *lc = s_lc[w], *stc = s_st[w];
+    float *db = s_db[w], *cc = s_cc[w], *val = s_val[w], *pk = s_pklc[w];
+    int *lc = reinterpret_cast<int *>(s_pklc[w] + kPkMax), *stc = s_st[w];
+    float *sqf = s_pklc[w];                        // [448] squares of the mean-free fine window
+    double *ecf = reinterpret_cast<double *>(s_cc[w]);   // [7 * ncand] lagged energy of every (candidate, lag)
     double *sq = s_sq[w], *ec = s_ec[w];
 
     const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));
@@ -339,54 +381,102 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
             for (int q = 0; q < 14; ++q)
                 if (lane + 32 * q < total) db[lane + 32 * q] = raw[q] * 32768.0f;
         }
-        for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;
         __syncwarp();
+        // mean of the reference window: one left-to-right chain, computed by every lane from
+        // broadcast 128-bit reads
         float engr = 0.0f;
-        for (int j = 0; j < kWin; ++j) engr += db[j];
+#pragma unroll 6
+        for (int j = 0; j < kWin; j += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(db + j);
+            engr += v4.x;
+            engr += v4.y;
+            engr += v4.z;
+            engr += v4.w;
+        }
         engr /= kWin;
-        __syncwarp();
-        for (int t = lane; t < total; t += 32) db[t] = db[t] - engr;
-        __syncwarp();
-        // window energies in ONE pass: lanes < ncand sum their candidate's first lagged window, lane 31
-        // sums the reference window (each still a single left-to-right float chain)
+        // first lag of every candidate's 7-lag window (the lists themselves are not needed again
+        // before pick_candidates rewrites them, so their storage holds the squares below)
         int my_st = 0;
         if (lane < ncand) {
             my_st = lc[lane] - 3;
             if (my_st < start0) my_st = start0;
             stc[lane] = my_st;
         }
+        __syncwarp();
+        for (int t = lane; t < total; t += 32) {
+            const float v = db[t] - engr;
+            db[t] = v;
+            sqf[t] = v * v;
+        }
+        __syncwarp();
+        // window energies in ONE pass: lanes < ncand sum their candidate's first lagged window, lane 31
+        // sums the reference window (each still a single left-to-right float chain)
         float s2 = 0.0f;
         if (lane < ncand || lane == 31) {
-            const float *q = db + my_st;
-            for (int j = 0; j < kWin; ++j) { const float st = q[j]; s2 += st * st; }
+            const float *q = sqf + my_st;
+#pragma unroll 8
+            for (int j = 0; j < kWin; ++j) s2 += q[j];
         }
         engr = __shfl_sync(0xffffffffu, s2, 31);
         maxval = 0.0f;
         if (engr > 0.0f) {
             float vmax = 0.0f;
-            for (int wk = lane; wk < ncand * 7; wk += 32) {
-                const int c = wk / 7, t = wk - 7 * c;
-                const float *dsp = db + stc[c] + t;
-                float dot = 0.0f;
-#pragma unroll 8
-                for (int j = 0; j < kWin; ++j) dot += db[j] * dsp[j];
-                val[wk] = dot;
-            }
-            __syncwarp();
-            if (lane < ncand) {
-                const int st = my_st;
-                double engc = s2;
-                for (int t = 0; t < 7; ++t) {
-                    if (engc < 1.0) engc = 1.0;
-                    const float dot = val[lane * 7 + t];
-                    const float v = static_cast<float>(dot / sqrt(10000.0 + (engc * engr)));
-                    val[lane * 7 + t] = v;
-                    vmax = fmaxf(vmax, v);
-                    const float a0 = db[st + t], az = db[st + t + kWin];
-                    engc -= static_cast<double>(a0 * a0);
-                    engc += static_cast<double>(az * az);
+            // cross products, one left-to-right chain per (candidate, lag).  With more than 32 chains a
+            // lane takes two at once: the reference samples are read once (broadcast float4) and the
+            // two chains advance together as one packed multiply + add.
+            const int nwk = ncand * 7;
+            for (int wk0 = 0; wk0 < nwk; wk0 += 64) {
+                const int wa = wk0 + lane, wb = wa + 32;
+                const int ca = min(wa, nwk - 1) / 7, ta = min(wa, nwk - 1) - 7 * ca;
+                const float *pa = db + stc[ca] + ta;
+                if (wk0 + 32 < nwk) {
+                    const int cb = min(wb, nwk - 1) / 7, tb = min(wb, nwk - 1) - 7 * cb;
+                    const float *pb = db + stc[cb] + tb;
+                    p2 dot = p2pack(0.0f, 0.0f);
+#pragma unroll 2
+                    for (int j = 0; j < kWin; j += 4) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(db + j);
+                        dot = p2add(dot, p2mul(p2pack(r4.x, r4.x), p2pack(pa[j], pb[j])));
+                        dot = p2add(dot, p2mul(p2pack(r4.y, r4.y), p2pack(pa[j + 1], pb[j + 1])));
+                        dot = p2add(dot, p2mul(p2pack(r4.z, r4.z), p2pack(pa[j + 2], pb[j + 2])));
+                        dot = p2add(dot, p2mul(p2pack(r4.w, r4.w), p2pack(pa[j + 3], pb[j + 3])));
+                    }
+                    if (wa < nwk) val[wa] = p2lo(dot);
+                    if (wb < nwk) val[wb] = p2hi(dot);
+                } else {
+                    float dot = 0.0f;
+#pragma unroll 2
+                    for (int j = 0; j < kWin; j += 4) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(db + j);
+                        dot += r4.x * pa[j];
+                        dot += r4.y * pa[j + 1];
+                        dot += r4.z * pa[j + 2];
+                        dot += r4.w * pa[j + 3];
+                    }
+                    if (wa < nwk) val[wa] = dot;
                 }
             }
+            // lagged energies: a short sequential double chain per candidate ...
+            if (lane < ncand) {
+                const float *q = sqf + my_st;
+                double engc = s2;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    if (engc < 1.0) engc = 1.0;
+                    ecf[lane * 7 + t] = engc;
+                    engc -= static_cast<double>(q[t]);
+                    engc += static_cast<double>(q[t + kWin]);
+                }
+            }
+            __syncwarp();
+            // ... and the expensive part (double square root and division) spread over all lanes
+            for (int wk = lane; wk < nwk; wk += 32) {
+                const float v = static_cast<float>(val[wk] / sqrt(10000.0 + (ecf[wk] * engr)));
+                val[wk] = v;
+                vmax = fmaxf(vmax, v);
+            }
+            __syncwarp();
+            for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;      // (the energies lived here)
             __syncwarp();
             // windows are written in candidate order; later ones overwrite earlier ones
             for (int c = 0; c < ncand; ++c) {
@@ -395,6 +485,8 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
                 __syncwarp();
             }
             maxval = warp_max(vmax);       // max over every value computed (order independent)
+        } else {
+            for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;
         }
         __syncwarp();
         ncand = pick_candidates(cc, nlags0, start0, maxval, pk, lc, lane);
@@ -459,47 +551,6 @@ __device__ __forceinline__ void durbin18(const float *r, float *a_out, float *er
 #pragma unroll
     for (int i = 0; i < kLpcOrd; ++i) a_out[i] = a[i];
     *err = e;
-}
-
-// Packed FP32 (sm_100a: mul / fma.rn.f32x2 -> FMUL2 / FFMA2, one issue slot for two lanes).  This
-// file is compiled with --fmad=false because the original rounds every product before it is added;
-// the packed forms keep exactly that rounding while halving the instruction count of a multiply-add.
-// Pairs live in 64-bit registers (p2) so that they stay packed between uses.
-typedef unsigned long long p2;
-__device__ __forceinline__ p2 pk(float x, float y)
-{
-    p2 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
-    return r;
-}
-__device__ __forceinline__ float p2lo(p2 a)
-{
-    float x, y;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
-    return x;
-}
-__device__ __forceinline__ float p2hi(p2 a)
-{
-    float x, y;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
-    return y;
-}
-__device__ __forceinline__ p2 p2mul(p2 a, p2 b)
-{
-    p2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// a + b as fma(b, one, a) with `one` = 1.0f read from constant memory.  ptxas (12.9) contracts
-// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false and explicit rounding modifiers
-// (and still does when the 1 is a literal), which would skip the rounding of the product; an fma
-// whose multiplier it cannot see is never merged with the multiply that feeds it, and b * 1 + a
-// rounds exactly like a + b.  SASS: FMUL2 + FFMA2 R, R.F32x2, UR.F32, R.F32x2.
-__device__ __forceinline__ p2 p2add(p2 a, p2 b)
-{
-    p2 r;
-    asm("{.reg .b64 ro; mov.b64 ro, {%3,%3}; fma.rn.f32x2 %0, %2, ro, %1;}" : "=l"(r) : "l"(a), "l"(b), "f"(c_rapt.one));
-    return r;
 }
 
 // One THREAD per 30 ms window.  The 19 autocorrelation chains (lags 0..18) of a window all consume
@@ -568,7 +619,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     float rms = 0.0f;
     if (live) {
         float en = 0.0f;
-        const p2 npre = pk(-c_rapt.preemp, -c_rapt.preemp);
+        const p2 npre = p2pack(-c_rapt.preemp, -c_rapt.preemp);
         auto ldx = [&](int i) -> p2 {                      // (x[b+i], x[b+i+1]), i even
             const int a = b + i;
             return *reinterpret_cast<const p2 *>(s_x + stat_skew(a));
@@ -584,7 +635,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
             en += p2lo(ff);
             en += p2hi(ff);
             const p2 t = p2mul(npre, xc);                                      // -(preemp * x[i])
-            const p2 d = p2mul(w.y, p2add(pk(p2hi(xc), p2lo(xn)), t));
+            const p2 d = p2mul(w.y, p2add(p2pack(p2hi(xc), p2lo(xn)), t));
             xc = xn;
             return d;
         };
@@ -593,22 +644,22 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
         for (int t = 0; t < 11; ++t) E[t] = produce2(2 * t);
 #pragma unroll
         for (int t = 0; t < 10; ++t) {
-            O[t] = pk(p2hi(E[t]), p2lo(E[t + 1]));
-            A[t] = pk(0.0f, 0.0f);
+            O[t] = p2pack(p2hi(E[t]), p2lo(E[t + 1]));
+            A[t] = p2pack(0.0f, 0.0f);
         }
-        O[10] = pk(0.0f, 0.0f);
+        O[10] = p2pack(0.0f, 0.0f);
         // 22 x 11 double steps = 484 samples; the ones past 478 are zeros and add nothing
         for (int jb = 0; jb < 22; ++jb) {
 #pragma unroll
             for (int st = 0; st < 11; ++st) {
                 const p2 cur = E[st];
-                const p2 d0 = pk(p2lo(cur), p2lo(cur)), d1 = pk(p2hi(cur), p2hi(cur));
+                const p2 d0 = p2pack(p2lo(cur), p2lo(cur)), d1 = p2pack(p2hi(cur), p2hi(cur));
 #pragma unroll
                 for (int t = 0; t < 10; ++t) A[t] = p2add(A[t], p2mul(d0, E[(st + t) % 11]));
 #pragma unroll
                 for (int t = 0; t < 10; ++t) A[t] = p2add(A[t], p2mul(d1, O[(st + t) % 11]));
                 const p2 nw = produce2(22 * jb + 2 * st + 22);
-                O[(st + 10) % 11] = pk(p2hi(E[(st + 10) % 11]), p2lo(nw));
+                O[(st + 10) % 11] = p2pack(p2hi(E[(st + 10) % 11]), p2lo(nw));
                 E[st] = nw;
             }
         }
