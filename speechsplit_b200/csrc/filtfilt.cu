@@ -198,7 +198,7 @@ template <> struct RawType<SSFE_I16, 0> { using T = short; };
 template <> struct RawType<SSFE_F32, 0> { using T = float; };
 
 template <int DTYPE, int PASS, bool FINAL>
-__global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
+__global__ void __launch_bounds__(kFiltWarps * 32, 4) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
                                                                      int n_tiles)
 {
     __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
@@ -253,19 +253,47 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
         if (PASS == 0) return (js >= kPadLen) && (js + 31 * kChunk + kTileW <= kPadLen + L);
         return js + 31 * kChunk + kTileW <= M;
     };
-    auto issue = [&](int sub) {
+    // Edge tiles (the first tile of an utterance touches the 18 reflected samples, the last one is
+    // ragged) are a third of all tiles for 3 s utterances, so they get the same treatment: every
+    // position is mapped to a clamped source index, the 32 loads go out together, and extension,
+    // appended sample and validity are applied afterwards from the index arithmetic alone.
+    auto src_index = [&](int j) -> int {                 // position in the extended signal -> sample of x'
+        int nn = j - kPadLen;
+        if (j < kPadLen) nn = kPadLen - j;
+        else if (j >= kPadLen + Lf) nn = Lf - 2 - (j - kPadLen - Lf);
+        return nn;
+    };
+    auto issue = [&](int sub, bool fast_path) {
         const int js = jt + sub * kTileW;
         if (PASS == 0) {
-            const RawT *xs = static_cast<const RawT *>(p.x) + (xbase + (js - kPadLen) + lane);
+            if (fast_path) {
+                const RawT *xs = static_cast<const RawT *>(p.x) + (xbase + (js - kPadLen) + lane);
 #pragma unroll
-            for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
+                for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
+            } else {
+                const RawT *xs = static_cast<const RawT *>(p.x) + xbase;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) raw[r] = xs[min(max(src_index(js + r * kChunk + lane), 0), L - 1)];
+            }
         } else {
-            const double *ys = y1 + (M - 1 - js - lane);             // reversed: row r is kChunk samples earlier
+            if (fast_path) {
+                const double *ys = y1 + (M - 1 - js - lane);         // reversed: row r is kChunk samples earlier
 #pragma unroll
-            for (int r = 0; r < 32; ++r) raw[r] = static_cast<RawT>(ys[-r * kChunk]);
+                for (int r = 0; r < 32; ++r) raw[r] = static_cast<RawT>(ys[-r * kChunk]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    raw[r] = static_cast<RawT>(y1[min(max(M - 1 - (js + r * kChunk + lane), 0), M - 1)]);
+            }
         }
     };
-    if (is_fast(0)) issue(0);
+    // the two samples the odd extension reflects about (x'[0], x'[Lf-1])
+    double e0 = 0.0, e1 = 0.0;
+    if (PASS == 0) {
+        e0 = fixed_sample<DTYPE>(p.x, xbase, L, 0);
+        e1 = fixed_sample<DTYPE>(p.x, xbase, L, Lf - 1);
+    }
+    issue(0, is_fast(0));
     for (int sub = 0; sub < kChunk / kTileW; ++sub) {
         const int jsub = jt + sub * kTileW;
         const bool fast = is_fast(sub);
@@ -277,17 +305,21 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
                 tl[r * kTileStride + lane] = v;
             }
         } else {
-            for (int r = 0; r < rows; ++r) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
                 const int j = jsub + r * kChunk + lane;
-                double v = 0.0;
-                if (j < M) {
-                    if (PASS == 0) v = ext_sample<DTYPE>(p.x, xbase, L, Lf, j);
-                    else v = y1[M - 1 - j];
+                double v = static_cast<double>(raw[r]);
+                if (PASS == 0) {
+                    if (DTYPE == SSFE_I16) v *= (1.0 / 32768.0);
+                    if (src_index(j) >= L) v = 1e-06;                          // the appended sample
+                    if (j < kPadLen) v = __dsub_rn(2.0 * e0, v);
+                    else if (j >= kPadLen + Lf) v = __dsub_rn(2.0 * e1, v);
                 }
+                if (r >= rows || j >= M) v = 0.0;
                 tl[r * kTileStride + lane] = v;
             }
         }
-        if (sub + 1 < kChunk / kTileW && is_fast(sub + 1)) issue(sub + 1);     // in flight during the recurrence
+        if (sub + 1 < kChunk / kTileW) issue(sub + 1, is_fast(sub + 1));       // in flight during the recurrence
         __syncwarp();
         // ---- recurrence: this lane's chunk is row `lane` -------------------------------------------
         if (run) {
@@ -331,6 +363,28 @@ __global__ void __launch_bounds__(kFiltWarps * 32) filt_tile_kernel(const FiltPa
                         const double y = tl[(16 * h + r) * kTileStride + lane];
                         const double d = __dmul_rn(__dsub_rn(mt_raw_to_double(raw[r]), 0.5), c_filt.dither_scale);
                         wavp[n0 - (16 * h + r) * kChunk] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), d));
+                    }
+                }
+            } else if (PASS == 1 && dith && p.dith_raw && wavp && !p.y && !p.wav && !p.wav64) {
+                // edge tile of the production path: same combine, dither words fetched together
+                const uint2 *d2 = reinterpret_cast<const uint2 *>(dith);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint2 dr[16];
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int nidx = M - 1 - kPadLen - (jsub + (16 * h + r) * kChunk + lane);
+                        dr[r] = d2[min(max(nidx, 0), Lf - 1)];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int j = jsub + (16 * h + r) * kChunk + lane;
+                        const int nidx = M - 1 - kPadLen - j;
+                        if (16 * h + r < rows && j < M && nidx >= 0 && nidx < Lf) {
+                            const double y = tl[(16 * h + r) * kTileStride + lane];
+                            const double d = __dmul_rn(__dsub_rn(mt_raw_to_double(dr[r]), 0.5), c_filt.dither_scale);
+                            wavp[nidx] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), d));
+                        }
                     }
                 }
             } else {
