@@ -389,10 +389,8 @@ extern "C" int ssfe_rapt(ssfe_ctx *ctx, const float *wav_dev, const int64_t *off
 
 // ---- the whole hot loop (make_spect_f0.py:50-74) ----------------------------------------------
 namespace ssfe {
-// dith_pre: raw dither words already being generated for exactly this batch's fixed offsets (the
-// caller ran rand_run on the side stream); nullptr = generate here.
 int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dtype, const ssfe_outputs *o,
-                   const std::vector<int64_t> &fix, const std::vector<int64_t> &foff, double *dith_pre = nullptr)
+                   const std::vector<int64_t> &fix, const std::vector<int64_t> &foff)
 {
     const int n = b->n_utts;
     // padded segment layout of the dithered wav
@@ -412,14 +410,14 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     int rc;
     if ((rc = check_ranges(ctx, b->f0_lo, b->f0_hi, n))) return rc;
     if ((rc = ensure(ctx, ctx->ws.wavp, (pos + kSegSlack) * sizeof(float)))) return rc;
-    if (!dith_pre && (rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
     float *wavp = static_cast<float *>(ctx->ws.wavp.p);
-    double *dith = dith_pre ? dith_pre : static_cast<double *>(ctx->ws.dith.p);
+    double *dith = static_cast<double *>(ctx->ws.dith.p);
 
     // the dither stream is independent of the signal until the very last filtfilt kernel: generate
     // it on a side stream while the forward / backward-local passes run
     mark(ctx, ST_RAND);
-    if (!dith_pre && (rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
+    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
     mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
@@ -432,7 +430,6 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     fo.wav64 = o->wav64;
     fo.dith_ready = ctx->ev_join;
     fo.dith_raw = true;
-    fo.keep_dith = dith_pre != nullptr;     // the caller releases the shared dither buffer after its last chunk
     if ((rc = filtfilt_run(ctx, x_dev, dtype, b->sample_offsets, fix.data(), n, fo))) return rc;
     mark(ctx, ST_EDGES);
     if ((rc = fill_reflect_edges(ctx, wavp, d_seg, d_fix, n))) return rc;

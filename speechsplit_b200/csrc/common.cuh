@@ -163,7 +163,6 @@ struct FiltOut {
     float *wav = nullptr;            // flat f32 [fixed offsets]
     double *wav64 = nullptr;
     cudaEvent_t dith_ready = nullptr; // waited on right before the kernel that reads `dith`
-    bool keep_dith = false;           // do not signal "dither buffer free" after this call
 };
 int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_off_host,
                  const int64_t *fix_off_host, int n, const FiltOut &out);
@@ -171,9 +170,10 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
                        const int64_t *fix_off_dev, int n);
 
 // launch_on: nullptr / ctx->stream = public path (doubles out); ctx->aux = side stream, raw word pairs
-// out, ordering handled inside.  gate: wait for ev_mt_go (start beside the previous call's Viterbi kernel).
+// out, ordering handled inside (waits for ev_dith_free and ev_mt_go: starts beside the previous call's
+// Viterbi kernel).
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
-             int n, double *u_dev, cudaStream_t launch_on = nullptr, bool gate = true);
+             int n, double *u_dev, cudaStream_t launch_on = nullptr);
 
 int init_rapt(ssfe_ctx *ctx);
 void free_rapt(ssfe_ctx *ctx);

@@ -633,7 +633,7 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 }
 
 template <int DTYPE>
-static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready, bool keep_dith,
+static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready,
                           const int *tile_off, int n_tiles, bool any_long)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
@@ -669,7 +669,7 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     if (sequential) filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
     else filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
     SSFE_LAUNCHED(ctx);
-    if (dith_ready && !keep_dith) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));   // the dither buffer may be refilled
+    if (dith_ready) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));   // the dither buffer may be refilled
     return SSFE_OK;
 }
 
@@ -729,9 +729,9 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.wav64 = out.wav64;
     p.y1_out = static_cast<double *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles, any_long);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles, any_long);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, out.keep_dith, d_tile_off, n_tiles, any_long);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, any_long);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, any_long);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, any_long);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }

@@ -798,12 +798,14 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
             const float uv_from_v = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr);
             float errmin = FLT_MAX;
             int minloc = 0;
-#pragma unroll
-            for (int j = 0; j < kCMax; ++j) {
+            // only the previous frame's live candidates are visited (typically 3-5 of the 20 slots;
+            // the count is warp-uniform, so the shuffles sit inside the loop)
+#pragma unroll 2
+            for (int j = 0; j < ncandp; ++j) {
                 const int loc1 = __shfl_sync(full_mask, loc_prev, j);
                 const float dp = __shfl_sync(full_mask, d_prev, j);
                 const double lg1 = __shfl_sync(full_mask, lg_prev, j);
-                if (j < ncandp) {
+                {
                     float ferr;
                     if (loc > 0) {
                         if (loc1 > 0) {
