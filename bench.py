@@ -354,7 +354,7 @@ def run_ours(args):
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "traffic": None, "frames_per_launch": T, "bytes_per_frame": BYTES_PER_FRAME,
                 "launch_ms": stft_ms, "fft_tflops_nominal": T * FLOP_PER_FRAME_FFT / (stft_ms * 1e-3) / 1e12,
-                "note": "FP32-issue bound, not HBM bound (DESIGN.md 5): 1344 B/frame vs ~1k warp instructions"}
+                "note": "issue / shared-memory bound, not HBM bound (DESIGN.md 5): 1344 B/frame vs ~790 warp instructions and 322 shared-memory wavefronts"}
     tr = os.path.join(ROOT, "profiles", "stft_traffic.json")
     if os.path.exists(tr):
         try:

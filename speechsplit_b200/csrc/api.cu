@@ -61,6 +61,7 @@ int stage_copy(ssfe_ctx *ctx, void *dst_dev, const void *src_pinned, size_t byte
     if (n16 == 0) return SSFE_OK;
     const unsigned grid = static_cast<unsigned>(std::min<size_t>((n16 + 255) / 256, 4 * static_cast<size_t>(ctx->num_sms)));
     meta_copy_kernel<<<grid, 256, 0, st>>>(static_cast<uint4 *>(dst_dev), static_cast<const uint4 *>(src_pinned), n16);
+    ctx->launches++;
     return cudaGetLastError() == cudaSuccess ? SSFE_OK : SSFE_ERR_CUDA;
 }
 

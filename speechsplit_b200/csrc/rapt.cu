@@ -562,6 +562,9 @@ __device__ __forceinline__ void durbin18(const float *r, float *a_out, float *er
 // odd-aligned pairs O for odd j; both are rings of 11 register pairs, refilled by one packed
 // produce step (window, pre-emphasis, energy) per two samples.  20 packed + ~3 move instructions
 // per sample instead of 38 scalar ones.
+// (Packing the previous and the current window of one frame into the two halves instead - all operands
+// naturally paired, 29 instructions per window sample, no moves - was measured too: a thread per FRAME
+// leaves room for only 5 warps per SM beside the 35 KB staged span, and the kernel took 21.9 ms.)
 // A CTA covers 32 consecutive frames of one utterance: warp 0 takes the current windows
 // (x + 256 g - 80), warp 1 the previous ones (x + 256 g - 400); the signal span is staged once
 // in shared memory (scaled by 32768, two pad words per 256 samples -> conflict-free 64-bit column reads).
