@@ -93,47 +93,111 @@ struct RaptParams {
     float *out;                    // log-F0
 };
 
-// ---- K1 ------------------------------------------------------------------------------------
-// 256 consecutive 2 kHz outputs of one utterance per CTA (n_ds is padded to a multiple of 256).  The
-// 2121 input samples are staged once, scaled by 32768, in shared memory as 8 phase rows: sample i
-// sits at row i % 8, column i / 8.  Output t needs samples 8 t + j, i.e. row j % 8, column t + j / 8:
-// for a fixed tap the threads of a warp read consecutive words (no conflicts, immediate offsets).
-// The row pitch is 4 mod 32 so that the coalesced staging stores (8 rows x 4 columns per warp) hit
-// 32 different banks as well.
-constexpr int kDecTile = 256;
-constexpr int kDecIn = kDec * (kDecTile - 1) + kNco;          // 2121
-constexpr int kDecPitch = 292;                                // >= 266 columns, == 4 (mod 32)
-
-__global__ void __launch_bounds__(kDecTile) rapt_decimate_kernel(const RaptParams p)
+// Packed FP32 (sm_100a: mul / fma.rn.f32x2 -> FMUL2 / FFMA2, one issue slot for two lanes).  This
+// file is compiled with --fmad=false because the original rounds every product before it is added;
+// the packed forms keep exactly that rounding while halving the instruction count of a multiply-add.
+// Pairs live in 64-bit registers (p2) so that they stay packed between uses.
+typedef unsigned long long p2;
+__device__ __forceinline__ p2 p2pack(float x, float y)
 {
-    __shared__ float s_x[kDec * kDecPitch];
+    p2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float p2lo(p2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return x;
+}
+__device__ __forceinline__ float p2hi(p2 a)
+{
+    float x, y;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return y;
+}
+__device__ __forceinline__ p2 p2mul(p2 a, p2 b)
+{
+    p2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a + b as fma(b, one, a) with `one` = 1.0f read from constant memory.  ptxas (12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false and explicit rounding modifiers
+// (and still does when the 1 is a literal), which would skip the rounding of the product; an fma
+// whose multiplier it cannot see is never merged with the multiply that feeds it, and b * 1 + a
+// rounds exactly like a + b.  SASS: FMUL2 + FFMA2 R, R.F32x2, UR.F32, R.F32x2.
+__device__ __forceinline__ p2 p2add(p2 a, p2 b)
+{
+    p2 r;
+    asm("{.reg .b64 ro; mov.b64 ro, {%3,%3}; fma.rn.f32x2 %0, %2, ro, %1;}" : "=l"(r) : "l"(a), "l"(b), "f"(c_rapt.one));
+    return r;
+}
+
+// ---- K1 ------------------------------------------------------------------------------------
+// 1024 consecutive 2 kHz outputs of one utterance per CTA (n_ds is padded to a multiple of 1024),
+// FOUR ADJACENT OUTPUTS PER THREAD.  Output o needs samples 8 o + j (j = 0..80), so tap j of output
+// o + 1 is tap j + 8 of output o: a thread walks its 105 samples once and feeds each to up to four
+// running sums - 26 shared-memory reads per output instead of 81 (the first version was bound by
+// exactly those reads).  The sums of outputs (o, o+1) and (o+2, o+3) advance as packed pairs with the
+// coefficient pairs (co[j], co[j-8]) from constant memory; every sum still takes its taps in
+// ascending order, product rounded before the add.
+// The 8265 input samples are staged once, scaled by 32768, as 8 phase rows (sample i at row i % 8,
+// column i / 8), the columns dealt round-robin to four sub-rows of odd pitch: thread t reads column
+// 4 t + m, i.e. sub-row m % 4, word t + m / 4 - consecutive threads, consecutive words - and the
+// coalesced staging stores hit 32 different banks as well.
+constexpr int kDecTile = 1024;
+constexpr int kDecThreads = kDecTile / 4;
+constexpr int kDecIn = kDec * (kDecTile - 1) + kNco;          // 8265
+constexpr int kDecSpan = kNco + 3 * kDec;                     // 105 samples per thread
+constexpr int kDecP4 = 261;                                   // words per sub-row (>= 259, odd)
+__constant__ float2 c_dec_pair[kDecSpan + 16];                // [i + 16] = (co[i], co[i - 8]), zero outside 0..80
+
+__global__ void __launch_bounds__(kDecThreads) rapt_decimate_kernel(const RaptParams p)
+{
+    __shared__ float s_x[kDec * 4 * kDecP4];
     const long long gid0 = blockIdx.x * static_cast<long long>(kDecTile);
     const int u = find_segment(p.ds_offs, p.n, gid0);
     const RaptUtt ut = p.utts[u];
     const int m0 = static_cast<int>(gid0 - ut.ds_off);
     const float *x = p.wav + ut.wav_off;
     const int base = kDec * m0 - (kNco / 2);
-    {   // all loads of a thread in flight together (clamped index, select afterwards)
-        constexpr int kPer = (kDecIn + kDecTile - 1) / kDecTile;     // 9
-        float raw[kPer];
+    // staging: all loads of a round in flight together (clamped index, select afterwards)
+    constexpr int kRound = 11, kRounds = (kDecIn + kRound * kDecThreads - 1) / (kRound * kDecThreads);   // 3 x 11 x 256
+#pragma unroll 1
+    for (int rd = 0; rd < kRounds; ++rd) {
+        float raw[kRound];
 #pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-            const int idx = base + threadIdx.x + q * kDecTile;
+        for (int q = 0; q < kRound; ++q) {
+            const int idx = base + (rd * kRound + q) * kDecThreads + threadIdx.x;
             raw[q] = x[min(max(idx, 0), ut.L - 1)];
         }
 #pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-            const int i = threadIdx.x + q * kDecTile, idx = base + i;
-            if (i < kDecIn) s_x[(i & (kDec - 1)) * kDecPitch + (i >> 3)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+        for (int q = 0; q < kRound; ++q) {
+            const int i = (rd * kRound + q) * kDecThreads + threadIdx.x, idx = base + i;
+            const int col = i >> 3;
+            if (i < kDecIn)
+                s_x[((i & 7) * 4 + (col & 3)) * kDecP4 + (col >> 2)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
         }
     }
     __syncthreads();
-    const float *col = s_x + threadIdx.x;
-    float sum = 0.0f;
+    const float *col0 = s_x + threadIdx.x;
+    p2 s01 = p2pack(0.0f, 0.0f), s23 = p2pack(0.0f, 0.0f);
 #pragma unroll
-    for (int j = 0; j < kNco; ++j) sum += c_rapt.co[j] * col[(j & (kDec - 1)) * kDecPitch + (j >> 3)];
-    p.ds[gid0 + threadIdx.x] =
-        static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
+    for (int i = 0; i < kDecSpan; ++i) {
+        const int m = i >> 3;
+        const float xv = col0[((i & 7) * 4 + (m & 3)) * kDecP4 + (m >> 2)];
+        const p2 xx = p2pack(xv, xv);
+        if (i <= kNco - 1 + kDec)                             // outputs o, o+1: taps i, i-8
+            s01 = p2add(s01, p2mul(xx, *reinterpret_cast<const p2 *>(&c_dec_pair[i + 16])));
+        if (i >= 2 * kDec)                                    // outputs o+2, o+3: taps i-16, i-24
+            s23 = p2add(s23, p2mul(xx, *reinterpret_cast<const p2 *>(&c_dec_pair[i])));
+    }
+    auto rnd = [](float sum) {
+        return static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
+    };
+    *reinterpret_cast<float4 *>(p.ds + gid0 + 4 * threadIdx.x) =
+        make_float4(rnd(p2lo(s01)), rnd(p2hi(s01)), rnd(p2lo(s23)), rnd(p2hi(s23)));
 }
 
 // ---- warp helpers ----------------------------------------------------------------------------
@@ -192,47 +256,6 @@ __device__ __forceinline__ int prune_candidates(float *peaks, int *locs, int nca
     }
     __syncwarp();
     return kCMax - 1;
-}
-
-// Packed FP32 (sm_100a: mul / fma.rn.f32x2 -> FMUL2 / FFMA2, one issue slot for two lanes).  This
-// file is compiled with --fmad=false because the original rounds every product before it is added;
-// the packed forms keep exactly that rounding while halving the instruction count of a multiply-add.
-// Pairs live in 64-bit registers (p2) so that they stay packed between uses.
-typedef unsigned long long p2;
-__device__ __forceinline__ p2 p2pack(float x, float y)
-{
-    p2 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
-    return r;
-}
-__device__ __forceinline__ float p2lo(p2 a)
-{
-    float x, y;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
-    return x;
-}
-__device__ __forceinline__ float p2hi(p2 a)
-{
-    float x, y;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
-    return y;
-}
-__device__ __forceinline__ p2 p2mul(p2 a, p2 b)
-{
-    p2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// a + b as fma(b, one, a) with `one` = 1.0f read from constant memory.  ptxas (12.9) contracts
-// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false and explicit rounding modifiers
-// (and still does when the 1 is a literal), which would skip the rounding of the product; an fma
-// whose multiplier it cannot see is never merged with the multiply that feeds it, and b * 1 + a
-// rounds exactly like a + b.  SASS: FMUL2 + FFMA2 R, R.F32x2, UR.F32, R.F32x2.
-__device__ __forceinline__ p2 p2add(p2 a, p2 b)
-{
-    p2 r;
-    asm("{.reg .b64 ro; mov.b64 ro, {%3,%3}; fma.rn.f32x2 %0, %2, ro, %1;}" : "=l"(r) : "l"(a), "l"(b), "f"(c_rapt.one));
-    return r;
 }
 
 // ---- K2 ------------------------------------------------------------------------------------
@@ -1014,6 +1037,15 @@ int init_rapt(ssfe_ctx *ctx)
     SSFE_CUDA(ctx, cudaMemcpy(T->d_w479, w479.data(), kStatW * sizeof(float), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpy(T->d_w480, w480.data(), kStatW * sizeof(float), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_rapt, &h, sizeof(h)));
+    {   // coefficient pairs of the decimator: [i + 16] = (co[i], co[i - 8])
+        std::vector<float2> cp(kDecSpan + 16);
+        for (int k = 0; k < kDecSpan + 16; ++k) {
+            const int i = k - 16;
+            cp[k].x = (i >= 0 && i < kNco) ? h.co[i] : 0.0f;
+            cp[k].y = (i - 8 >= 0 && i - 8 < kNco) ? h.co[i - 8] : 0.0f;
+        }
+        SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_dec_pair, cp.data(), cp.size() * sizeof(float2)));
+    }
     SSFE_CUDA(ctx, cudaFuncSetAttribute(rapt_stat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kStatSmem)));
     return SSFE_OK;
@@ -1125,7 +1157,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     T->last_rr = p.rr;
 
     cudaStream_t st = ctx->stream;
-    rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecTile, 0, st>>>(p);
+    rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecThreads, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     mark(ctx, ST_RAPT_CAND);
     if (fr > 0) {
