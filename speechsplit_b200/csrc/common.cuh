@@ -27,7 +27,7 @@ struct DevBuf {
 // grow-only device scratch; growth happens during warm-up only
 struct Workspace {
     DevBuf wavp, y1, dith, meta_dev, tiles, misc;
-    DevBuf rapt_ds, rapt_cand, rapt_stat, rapt_f0;
+    DevBuf rapt_ds, rapt_cand, rapt_stat, rapt_f0, dec_map;
     DevBuf carry;
     DevBuf mt_state, mt_state_aux;     // segment start states of the dither streams (mt19937.cu)
 };

@@ -153,31 +153,57 @@ constexpr int kDecSpan = kNco + 3 * kDec;                     // 105 samples per
 constexpr int kDecP4 = 261;                                   // words per sub-row (>= 259, odd)
 __constant__ float2 c_dec_pair[kDecSpan + 16];                // [i + 16] = (co[i], co[i - 8]), zero outside 0..80
 
-__global__ void __launch_bounds__(kDecThreads) rapt_decimate_kernel(const RaptParams p)
+// tile -> utterance, written once per call by one thread per utterance: the decimator's CTAs are short
+// (a binary search over the offsets at the start of each was 46 % of its stall samples)
+__global__ void rapt_tile_map_kernel(const long long *__restrict__ ds_offs, int n, int *__restrict__ map)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int t1 = static_cast<int>(ds_offs[u + 1] / kDecTile);
+    for (int t = static_cast<int>(ds_offs[u] / kDecTile); t < t1; ++t) map[t] = u;
+}
+
+__global__ void __launch_bounds__(kDecThreads) rapt_decimate_kernel(const RaptParams p, const int *__restrict__ tile_map)
 {
     __shared__ float s_x[kDec * 4 * kDecP4];
     const long long gid0 = blockIdx.x * static_cast<long long>(kDecTile);
-    const int u = find_segment(p.ds_offs, p.n, gid0);
+    const int u = tile_map[blockIdx.x];
     const RaptUtt ut = p.utts[u];
     const int m0 = static_cast<int>(gid0 - ut.ds_off);
     const float *x = p.wav + ut.wav_off;
     const int base = kDec * m0 - (kNco / 2);
-    // staging: all loads of a round in flight together (clamped index, select afterwards)
+    // Staging.  Thread t owns samples i = t + 256 k: its phase row (i % 8) and sub-row ((i / 8) % 4) never
+    // change, only the word advances by 8 per k.  Interior tiles need no clamping; edge tiles load through
+    // clamped indices and select afterwards.  All loads of a round are in flight together.
+    const int tid = threadIdx.x;
+    float *srow = s_x + ((tid & 7) * 4 + ((tid >> 3) & 3)) * kDecP4 + (tid >> 5);
     constexpr int kRound = 11, kRounds = (kDecIn + kRound * kDecThreads - 1) / (kRound * kDecThreads);   // 3 x 11 x 256
+    const bool interior = base >= 0 && base + kRounds * kRound * kDecThreads <= ut.L;
+    if (interior) {
+        const float *xs = x + base + tid;
 #pragma unroll 1
-    for (int rd = 0; rd < kRounds; ++rd) {
-        float raw[kRound];
+        for (int rd = 0; rd < kRounds; ++rd) {
+            float raw[kRound];
 #pragma unroll
-        for (int q = 0; q < kRound; ++q) {
-            const int idx = base + (rd * kRound + q) * kDecThreads + threadIdx.x;
-            raw[q] = x[min(max(idx, 0), ut.L - 1)];
+            for (int q = 0; q < kRound; ++q) raw[q] = xs[(rd * kRound + q) * kDecThreads];
+#pragma unroll
+            for (int q = 0; q < kRound; ++q)
+                if ((rd * kRound + q) * kDecThreads + tid < kDecIn) srow[(rd * kRound + q) * 8] = raw[q] * 32768.0f;
         }
+    } else {
+#pragma unroll 1
+        for (int rd = 0; rd < kRounds; ++rd) {
+            float raw[kRound];
 #pragma unroll
-        for (int q = 0; q < kRound; ++q) {
-            const int i = (rd * kRound + q) * kDecThreads + threadIdx.x, idx = base + i;
-            const int col = i >> 3;
-            if (i < kDecIn)
-                s_x[((i & 7) * 4 + (col & 3)) * kDecP4 + (col >> 2)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+            for (int q = 0; q < kRound; ++q) {
+                const int idx = base + (rd * kRound + q) * kDecThreads + tid;
+                raw[q] = x[min(max(idx, 0), ut.L - 1)];
+            }
+#pragma unroll
+            for (int q = 0; q < kRound; ++q) {
+                const int i = (rd * kRound + q) * kDecThreads + tid, idx = base + i;
+                if (i < kDecIn) srow[(rd * kRound + q) * 8] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+            }
         }
     }
     __syncthreads();
@@ -1115,6 +1141,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
 
     int rc;
     if ((rc = ensure(ctx, ctx->ws.rapt_ds, dsn * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->ws.dec_map, (dsn / kDecTile + 1) * sizeof(int)))) return rc;
+    int *dec_map = static_cast<int *>(ctx->ws.dec_map.p);
     const size_t per_fr = kCMax * (sizeof(short) + 2 * sizeof(float)) + 2 * sizeof(float) + 8;
     if ((rc = ensure(ctx, ctx->ws.rapt_cand, (fr + 8) * per_fr))) return rc;
 
@@ -1157,7 +1185,9 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     T->last_rr = p.rr;
 
     cudaStream_t st = ctx->stream;
-    rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecThreads, 0, st>>>(p);
+    rapt_tile_map_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p.ds_offs, n, dec_map);
+    SSFE_LAUNCHED(ctx);
+    rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecThreads, 0, st>>>(p, dec_map);
     SSFE_LAUNCHED(ctx);
     mark(ctx, ST_RAPT_CAND);
     if (fr > 0) {
