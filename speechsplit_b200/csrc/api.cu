@@ -271,7 +271,7 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     free_rapt(ctx);
     Workspace &w = ctx->ws;
     DevBuf *all[] = {&w.wavp, &w.y1, &w.dith, &w.meta_dev, &w.tiles, &w.misc, &w.rapt_ds, &w.rapt_cand,
-                     &w.rapt_stat, &w.rapt_f0, &w.dec_map, &w.carry, &w.mt_state, &w.mt_state_aux, &ctx->h_x, &ctx->h_mel, &ctx->h_f0, &ctx->h_bins};
+                     &w.rapt_stat, &w.rapt_f0, &w.dec_map, &w.cand_map, &w.stat_map, &w.filt_map, &w.carry, &w.mt_state, &w.mt_state_aux, &ctx->h_x, &ctx->h_mel, &ctx->h_f0, &ctx->h_bins};
     for (DevBuf *b : all) free_buf(*b);
     if (ctx->mt_taps) cudaFree(ctx->mt_taps);
     if (ctx->meta_host) cudaFreeHost(ctx->meta_host);

@@ -27,7 +27,7 @@ struct DevBuf {
 // grow-only device scratch; growth happens during warm-up only
 struct Workspace {
     DevBuf wavp, y1, dith, meta_dev, tiles, misc;
-    DevBuf rapt_ds, rapt_cand, rapt_stat, rapt_f0, dec_map;
+    DevBuf rapt_ds, rapt_cand, rapt_stat, rapt_f0, dec_map, cand_map, stat_map, filt_map;
     DevBuf carry;
     DevBuf mt_state, mt_state_aux;     // segment start states of the dither streams (mt19937.cu)
 };
@@ -127,6 +127,17 @@ inline T *upload(ssfe_ctx *ctx, const T *host, size_t n)
         cudaError_t e__ = cudaGetLastError();                           \
         if (e__ != cudaSuccess) return ::ssfe::cuda_fail(ctx, e__, "kernel launch"); \
     } while (0)
+
+// map[t] = u for every tile t in [off[u] / unit, off[u+1] / unit): one thread per segment writes the
+// lookup that the per-tile kernels would otherwise redo as a 14-step binary search of dependent loads
+template <typename T>
+__global__ void segment_map_kernel(const T *__restrict__ off, int n, long long unit, int *__restrict__ map)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const long long t1 = static_cast<long long>(off[u + 1]) / unit;
+    for (long long t = static_cast<long long>(off[u]) / unit; t < t1; ++t) map[t] = u;
+}
 
 // index of the segment containing pos: largest i with off[i] <= pos (off has n+1 entries)
 template <typename T>

@@ -199,14 +199,14 @@ template <> struct RawType<SSFE_F32, 0> { using T = float; };
 
 template <int DTYPE, int PASS, bool FINAL>
 __global__ void __launch_bounds__(kFiltWarps * 32, 4) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
-                                                                     int n_tiles)
+                                                                     int n_tiles, const int *__restrict__ tile_map)
 {
     __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tile = blockIdx.x * kFiltWarps + w;
     if (tile >= n_tiles) return;
     double *tl = s_tile[w];
-    const int u = find_segment(tile_off, p.n, tile);
+    const int u = tile_map[tile];
     const int sc = tile - tile_off[u];                         // super-chunk (32 chunks) inside the utterance
     const int nch = p.chunk_off[u + 1] - p.chunk_off[u];
     const int c = sc * 32 + lane;                              // this lane's chunk
@@ -634,14 +634,14 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 
 template <int DTYPE>
 static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready,
-                          const int *tile_off, int n_tiles, bool any_long)
+                          const int *tile_off, int n_tiles, const int *tile_map, bool any_long)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
     const unsigned gu = (p.n + 63) / 64;
     cudaStream_t st = ctx->stream;
     if (!sequential) {
-        filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
+        filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
         SSFE_LAUNCHED(ctx);
     }
     const unsigned gw = (p.n + kCarryWarps - 1) / kCarryWarps;
@@ -652,11 +652,11 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
         SSFE_LAUNCHED(ctx);
     }
     if (sequential) filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
-    else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
+    else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     p.y1 = p.y1_out;
     if (!sequential) {
-        filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
+        filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
         SSFE_LAUNCHED(ctx);
     }
     filt_carry_kernel<DTYPE, 1><<<gu, 64, 0, st>>>(p);
@@ -667,7 +667,7 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     }
     if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
     if (sequential) filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
-    else filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles);
+    else filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     if (dith_ready) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));   // the dither buffer may be refilled
     return SSFE_OK;
@@ -715,6 +715,15 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     const int *d_tile_off = upload(ctx, tile_off.data(), n + 1);
     if (!p.in_off || !p.fix_off || !p.chunk_off || !d_tile_off) return SSFE_ERR_NOMEM;
     const int n_tiles = static_cast<int>(tiles);
+    {
+        const int rc_map = ensure(ctx, ctx->ws.filt_map, (tiles + 1) * sizeof(int));
+        if (rc_map) return rc_map;
+    }
+    int *d_tile_map = static_cast<int *>(ctx->ws.filt_map.p);
+    if (!sequential) {
+        segment_map_kernel<int><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(d_tile_off, n, 1, d_tile_map);
+        SSFE_LAUNCHED(ctx);
+    }
     p.n = n;
     p.n_chunks = static_cast<int>(chunks);
     p.chunk_len = sequential ? static_cast<int>(std::min<int64_t>(max_m, 0x7fffffff)) : kChunk;
@@ -729,9 +738,9 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.wav64 = out.wav64;
     p.y1_out = static_cast<double *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, any_long);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, any_long);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, any_long);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }

@@ -153,16 +153,8 @@ constexpr int kDecSpan = kNco + 3 * kDec;                     // 105 samples per
 constexpr int kDecP4 = 261;                                   // words per sub-row (>= 259, odd)
 __constant__ float2 c_dec_pair[kDecSpan + 16];                // [i + 16] = (co[i], co[i - 8]), zero outside 0..80
 
-// tile -> utterance, written once per call by one thread per utterance: the decimator's CTAs are short
-// (a binary search over the offsets at the start of each was 46 % of its stall samples)
-__global__ void rapt_tile_map_kernel(const long long *__restrict__ ds_offs, int n, int *__restrict__ map)
-{
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n) return;
-    const int t1 = static_cast<int>(ds_offs[u + 1] / kDecTile);
-    for (int t = static_cast<int>(ds_offs[u] / kDecTile); t < t1; ++t) map[t] = u;
-}
-
+// (tile -> utterance comes from segment_map_kernel: a binary search over the offsets at the start of each of
+// these short CTAs was 46 % of the stall samples)
 __global__ void __launch_bounds__(kDecThreads) rapt_decimate_kernel(const RaptParams p, const int *__restrict__ tile_map)
 {
     __shared__ float s_x[kDec * 4 * kDecP4];
@@ -289,7 +281,8 @@ constexpr int kCandWarps = 4;
 
 constexpr int kCandTile = 16;      // frames per CTA (one binary search per tile, 4 frames per warp)
 
-__global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off)
+__global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off,
+                                                                    const int *__restrict__ tile_map)
 {
     __shared__ __align__(16) float s_db[kCandWarps][448];
     __shared__ __align__(16) float s_cc[kCandWarps][kCcMax];        // fine stage: first the lagged energies (double[140])
@@ -307,7 +300,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
     double *ecf = reinterpret_cast<double *>(s_cc[w]);   // [7 * ncand] lagged energy of every (candidate, lag)
     double *sq = s_sq[w], *ec = s_ec[w];
 
-    const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));
+    const int u = tile_map[blockIdx.x];
     const RaptUtt ut = p.utts[u];
     const RaptCfg &cf = c_rapt.cfg[ut.cfg];
     const int g_tile = (static_cast<int>(blockIdx.x) - tile_off[u]) * kCandTile;
@@ -624,7 +617,8 @@ constexpr int kStatXWords = kStatSpanPad + 2 * (kStatSpanPad / 256) + 2;
 constexpr int kStatWinPairs = 256;                                            // window pairs (zero past 479 / 480)
 __device__ __forceinline__ int stat_skew(int i) { return i + 2 * (i >> 8); }
 
-__global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptParams p, const int *__restrict__ tile_off)
+__global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptParams p, const int *__restrict__ tile_off,
+                                                                    const int *__restrict__ tile_map)
 {
     extern __shared__ __align__(16) float s_stat[];
     float4 *s_w4 = reinterpret_cast<float4 *>(s_stat);      // [256] {w480[i], w480[i+1], w479[i], w479[i+1]}, i = 2q
@@ -632,7 +626,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     float *s_ex = s_x + kStatXWords;                        // [frames][20]: rho1[1..18], err1, rms1 of the previous window
 
     const int tid = threadIdx.x;
-    const int u = find_segment(tile_off, p.n, static_cast<int>(blockIdx.x));
+    const int u = tile_map[blockIdx.x];
     const RaptUtt ut = p.utts[u];
     const int g0 = (static_cast<int>(blockIdx.x) - tile_off[u]) * kStatFrames;
     const float *x = p.wav + ut.wav_off;
@@ -1143,6 +1137,9 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     if ((rc = ensure(ctx, ctx->ws.rapt_ds, dsn * sizeof(float)))) return rc;
     if ((rc = ensure(ctx, ctx->ws.dec_map, (dsn / kDecTile + 1) * sizeof(int)))) return rc;
     int *dec_map = static_cast<int *>(ctx->ws.dec_map.p);
+    if ((rc = ensure(ctx, ctx->ws.cand_map, (cand_tiles + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(ctx, ctx->ws.stat_map, (stat_tiles + 1) * sizeof(int)))) return rc;
+    int *cand_map = static_cast<int *>(ctx->ws.cand_map.p), *stat_map = static_cast<int *>(ctx->ws.stat_map.p);
     const size_t per_fr = kCMax * (sizeof(short) + 2 * sizeof(float)) + 2 * sizeof(float) + 8;
     if ((rc = ensure(ctx, ctx->ws.rapt_cand, (fr + 8) * per_fr))) return rc;
 
@@ -1185,16 +1182,20 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     T->last_rr = p.rr;
 
     cudaStream_t st = ctx->stream;
-    rapt_tile_map_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p.ds_offs, n, dec_map);
+    segment_map_kernel<long long><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p.ds_offs, n, kDecTile, dec_map);
+    SSFE_LAUNCHED(ctx);
+    segment_map_kernel<int><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_cand_tiles, n, 1, cand_map);
+    SSFE_LAUNCHED(ctx);
+    segment_map_kernel<int><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_stat_tiles, n, 1, stat_map);
     SSFE_LAUNCHED(ctx);
     rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecThreads, 0, st>>>(p, dec_map);
     SSFE_LAUNCHED(ctx);
     mark(ctx, ST_RAPT_CAND);
     if (fr > 0) {
-        rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles);
+        rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles, cand_map);
         SSFE_LAUNCHED(ctx);
         mark(ctx, ST_RAPT_STAT);
-        rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles);
+        rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles, stat_map);
         SSFE_LAUNCHED(ctx);
     } else {
         mark(ctx, ST_RAPT_STAT);
