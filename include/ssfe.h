@@ -210,6 +210,18 @@ int ssfe_collate(ssfe_ctx *ctx, const float *mel_dev, const float *f0_norm_dev,
                  float *melsp_dev /* [n,pad,80] */, float *pitch_dev /* [n,pad,1] */,
                  float *onehot_dev /* [n,pad,257] or NULL */, int64_t *bins_dev /* or NULL */);
 
+/* ---- "next" row: InterpLnr.forward in training mode (model.py:380-436) ---- */
+/* x_dev float32 [batch, T, C] (solver.py:160: mel and F0 concatenated, T = 192, C = 81), len_seq_dev
+ * int64 [batch]; the random draws of model.py:392-393 and :401-404 are inputs, all on the device:
+ * scales_dev float32 [batch * max_num_seg] in [0.5, 1.5), len_seg_dev int64 [batch * max_num_seg] in
+ * [min_len_seg, max_len_seg).  out_dev float32 [batch, max_len_pad, C]: the surviving resampled frames
+ * of every item in segment order, zero-padded / truncated at max_len_pad (pad_sequences, :366-377).
+ * One kernel, asynchronous on the context's stream - no host sync (the reference has one at :432).
+ * Position i0 + 1 of an item is only read where the reference's masks allow it (i0 < len_seq - 1 <= T - 1). */
+int ssfe_interp_lnr(ssfe_ctx *ctx, const float *x_dev, int batch, int T, int C, const int64_t *len_seq_dev,
+                    const float *scales_dev, const int64_t *len_seg_dev, int max_num_seg, int max_len_seg,
+                    int max_len_pad, float *out_dev);
+
 #ifdef __cplusplus
 }
 #endif

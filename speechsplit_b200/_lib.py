@@ -58,6 +58,8 @@ SIGNATURES = {
     "ssfe_plan_offsets": (ctypes.c_int, [c_i64p, ctypes.c_int, c_i64p, c_i64p]),
     "ssfe_filtfilt": (ctypes.c_int, [vp, vp, ctypes.c_int, c_i64p, ctypes.c_int, vp]),
     "ssfe_rand": (ctypes.c_int, [vp, c_u32p, c_u64p, c_i64p, ctypes.c_int, vp]),
+    "ssfe_interp_lnr": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, vp]),
     "ssfe_mt_charpoly_terms": (ctypes.c_int, [vp, ctypes.c_int]),
     "ssfe_mt_jump_poly": (ctypes.c_int, [ctypes.c_uint64, vp]),
     "ssfe_mt_jump_taps": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int]),

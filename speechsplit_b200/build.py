@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libssfe.so")
 OBJ = os.path.join(PKG, "_obj")
-CU = ["api.cu", "stft_mel.cu", "filtfilt.cu", "mt19937.cu", "f0_post.cu", "rapt.cu"]
+CU = ["api.cu", "stft_mel.cu", "filtfilt.cu", "mt19937.cu", "f0_post.cu", "rapt.cu", "interp.cu"]
 CPP = ["filt_consts.cpp", "mt_jump.cpp"]
 # RAPT reproduces the original's float evaluation order; fused multiply-adds would change it
 EXTRA = {"rapt.cu": ["--fmad=false"]}

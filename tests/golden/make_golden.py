@@ -9,6 +9,8 @@ What is reference-produced (pins the oracle and the CUDA path):
                      quantize_f0_torch, pad_seq_to_2 outputs of the reference's utils.py
   pipeline_*.npz     y / wav / D_mel-dB-normalised S of make_spect_f0.py:52-61 executed with the
                      reference's butter_highpass + pySTFT + scipy filtfilt + numpy RandomState
+  interp_lnr.npz     inputs, captured random draws and output of the reference's model.InterpLnr
+                     (model.py:380-436) in training mode
 What is NOT reference-produced (librosa / pysptk are absent):
   the mel basis (oracle/mel_basis.py restatement) used inside pipeline_*.npz, and the
   ``f0_rapt`` arrays (oracle/rapt_ref.c restatement) - stored as regression vectors and
@@ -108,8 +110,40 @@ def pipeline(name, metas):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+def interp_lnr():
+    """InterpLnr.forward of the reference's model.py (training mode), run on the CPU with a seeded
+    generator.  The two random tensors it draws (model.py:392-393, :401-404) are captured by making the
+    same two calls after the same seed - the module's forward then consumes the identical stream."""
+    import model as ref_model  # the reference's own module (needs only torch, numpy and utils)
+
+    class HP:
+        max_len_seq, max_len_pad, min_len_seg, max_len_seg = 128, 192, 19, 32
+
+    mod = ref_model.InterpLnr(HP)
+    mod.train()
+    out = {}
+    for k, (seed, B, C) in enumerate(((0, 4, 81), (7, 16, 8), (11, 3, 5))):
+        g = torch.Generator().manual_seed(1000 + seed)
+        x = torch.rand((B, HP.max_len_pad, C), generator=g, dtype=torch.float32)
+        len_seq = torch.randint(HP.max_len_seq // 2, HP.max_len_seq + 1, (B,), generator=g)
+        if k == 2:
+            len_seq[0] = 2                                   # degenerate: a single interpolation interval
+            len_seq[1] = HP.max_len_pad                      # longer than any draw can cover
+        torch.manual_seed(seed)
+        scales = torch.rand(B * mod.max_num_seg) + 0.5
+        len_seg = torch.randint(low=HP.min_len_seg, high=HP.max_len_seg, size=(B * mod.max_num_seg, 1))
+        torch.manual_seed(seed)
+        y = mod(x, len_seq)
+        out["x%d" % k], out["len_seq%d" % k] = x.numpy(), len_seq.numpy()
+        out["scales%d" % k], out["len_seg%d" % k] = scales.numpy(), len_seg.numpy().reshape(-1)
+        out["y%d" % k] = y.numpy()
+    out["n"] = 3
+    np.savez_compressed(os.path.join(HERE, "interp_lnr.npz"), **out)
+
+
 if __name__ == "__main__":
     utils_kat()
+    interp_lnr()
     # cfg1: one 3.000 s male utterance, speaker p226 (+ two more files of the same speaker so the
     # dither stream continuity and the L % 256 == 0 append path are pinned)
     pipeline("pipeline_p226.npz", [UttMeta("p226", "M", 0, 48000, 226000),

@@ -185,3 +185,52 @@ def test_extract_errors(fe):
         fe.extract(x, [0, 500], [50.0], [250.0], [226], [0])             # too short for get_f0
     with pytest.raises(ValueError):
         fe.extract(torch.zeros(5000, dtype=torch.int16), [0, 5000], [70.0], [250.0], [226], [0])   # not M / F
+
+
+def test_make_spect_f0_script_drop_in(tmp_path):
+    """The script form (speechsplit_b200.make_spect_f0) against the reference's loop run on the oracle:
+    a tree of 16-bit mono WAVs + spk2gen.pkl in, spmel/ and raptf0/ trees of NPY v1.0 '<f4' out
+    (make_spect_f0.py:19-31,47-74), files visited in sorted() order so that each speaker's dither
+    stream continues across its files."""
+    import pickle
+    import wave
+
+    from speechsplit_b200.make_spect_f0 import make_spect_f0
+
+    metas = make_manifest(2, 3, seed=23)
+    pcm = [p.numpy() for p in synth_batch(metas)]
+    root, out, out_f0 = tmp_path / "wavs", tmp_path / "spmel", tmp_path / "raptf0"
+    spk2gen = {}
+    for k, (m, p) in enumerate(zip(metas, pcm)):
+        (root / m.spk).mkdir(parents=True, exist_ok=True)
+        spk2gen[m.spk] = m.gender
+        # names chosen so that sorted() order differs from creation order within a speaker
+        with wave.open(str(root / m.spk / ("%s_%03d.wav" % (m.spk, 900 - k))), "wb") as w:
+            w.setnchannels(1), w.setsampwidth(2), w.setframerate(16000)
+            w.writeframes(p.astype("<i2").tobytes())
+    with open(tmp_path / "spk2gen.pkl", "wb") as f:
+        pickle.dump(spk2gen, f)
+
+    make_spect_f0(str(root), str(out), str(out_f0), str(tmp_path / "spk2gen.pkl"), verbose=False)
+
+    worst, same, total = 0.0, 0, 0
+    for spk in sorted(spk2gen):
+        files = sorted(os.listdir(root / spk))
+        prng = RandomState(int(spk[1:]))
+        for fname in files:
+            with wave.open(str(root / spk / fname), "rb") as w:
+                x = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+            S_ref, f0n_ref = rp.extract_utterance(pcm_to_float64(x), spk2gen[spk], prng)
+            mel_path, f0_path = out / spk / (fname[:-4] + ".npy"), out_f0 / spk / (fname[:-4] + ".npy")
+            with open(mel_path, "rb") as f:
+                head = f.read(10)
+            assert head[:6] == b"\x93NUMPY" and head[6:8] == b"\x01\x00"      # NPY v1.0 (allow_pickle=False)
+            S, f0n = np.load(mel_path, allow_pickle=False), np.load(f0_path, allow_pickle=False)
+            assert S.dtype == np.float32 and f0n.dtype == np.float32
+            assert S.shape == S_ref.shape and f0n.shape == f0n_ref.shape and S.shape[0] == f0n.shape[0]   # :69
+            worst = max(worst, float(np.abs(S - S_ref).max()))
+            b, b_ref = rp.quantize_f0_numpy(f0n)[1], rp.quantize_f0_numpy(f0n_ref.astype(np.float32))[1]
+            same += int((b == b_ref).sum())
+            total += b.size
+    assert worst <= 1e-4, worst
+    assert same / total >= 0.999, (same, total)

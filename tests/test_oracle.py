@@ -130,3 +130,13 @@ def test_rapt_debug_consistency():
     for i in range(T):                      # last candidate of every frame is the unvoiced one
         assert d["locs"][i, nc[i] - 1] == -1
         assert np.all(d["locs"][i, :nc[i] - 1] >= 27) and np.all(d["locs"][i, :nc[i] - 1] <= 160)
+
+
+def test_interp_lnr_oracle_matches_reference_module(golden_dir):
+    """oracle/interp_lnr.py vs the output of the reference's own model.InterpLnr (training mode,
+    model.py:380-436) for the same captured random draws: bit-identical."""
+    from oracle.interp_lnr import interp_lnr
+    z = np.load(os.path.join(golden_dir, "interp_lnr.npz"))
+    for k in range(int(z["n"])):
+        y = interp_lnr(z["x%d" % k], z["len_seq%d" % k], z["scales%d" % k], z["len_seg%d" % k])
+        assert y.dtype == np.float32 and np.array_equal(y, z["y%d" % k]), k
