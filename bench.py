@@ -316,11 +316,17 @@ def run_ours(args):
         frs = np.diff(fr)
         cand = np.nonzero(frs > 130)[0]
 
+        from speechsplit_b200.interp import InterpLnr
+        interp = InterpLnr().to(dev).train()
+
         def crop_step():
             utt = rng.choice(cand, 16)
             ln = rng.integers(64, 129, 16)
             left = np.array([rng.integers(0, frs[u] - l) for u, l in zip(utt, ln)])
-            return fe.collate(outs["mel"], outs["f0_norm"], fr, utt, left, ln, 192)
+            melsp, pitch, onehot, bins = fe.collate(outs["mel"], outs["f0_norm"], fr, utt, left, ln, 192)
+            # solver.py:160-161: the random-resampling augmentation of (mel, F0) - one kernel, no host sync
+            x_intrp = interp(torch.cat((melsp, pitch), dim=-1), torch.from_numpy(ln).to(dev))
+            return melsp, pitch, onehot, bins, x_intrp
 
         for _ in range(20):
             crop_step()
@@ -333,7 +339,8 @@ def run_ours(args):
         c1.record()
         torch.cuda.synchronize()
         collate = {"steps_per_s_device": 200 / (c0.elapsed_time(c1) * 1e-3), "steps_per_s_wall": 200 / (time.perf_counter() - t0),
-                   "batch": 16, "max_len_pad": 192}
+                   "batch": 16, "max_len_pad": 192,
+                   "step": "crop + clip + pad + one-hot (data_loader.py:101-128, solver.py:162) + InterpLnr (model.py:380-436)"}
 
     if rank != 0:
         if world > 1:
