@@ -231,7 +231,12 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
         if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
         if ((e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
-        if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
+        {   // the dither generator is a handful of latency chains on a side stream: when it competes with the big
+            // kernels for SM slots it has to win, or the backward filter pass waits for it (2 ms at 1/8 of the corpus)
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            if ((e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi_pri)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
+        }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_dith_free, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }

@@ -1195,16 +1195,18 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles, cand_map);
         SSFE_LAUNCHED(ctx);
         mark(ctx, ST_RAPT_STAT);
+        // The next call's dither generation (side stream, high priority) may start here: the stationarity
+        // kernel holds only 10 warps per SM, the Viterbi kernel and the F0 post-processing are latency /
+        // write bound, so its ~5 ms of work fit beside them - and at 1/8 of the corpus (one GPU of
+        // eight) its 1.5 ms segment walks need the head start to be done before the backward filter pass.
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
         rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles, stat_map);
         SSFE_LAUNCHED(ctx);
     } else {
         mark(ctx, ST_RAPT_STAT);
+        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
     }
     mark(ctx, ST_RAPT_DP);
-    // From here on the stream only runs latency- and memory-bound kernels (Viterbi, F0 post, then the
-    // next call's filtfilt passes): the place where the next call's dither walk, which needs issue
-    // slots on ~100 SMs for ~20 ms, costs the least.
-    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
     rapt_dp_kernel<<<static_cast<unsigned>((n + kDpWarps - 1) / kDpWarps), kDpWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     return SSFE_OK;
