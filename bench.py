@@ -121,11 +121,51 @@ def make_cpu_jobs(metas, pcm_of, per_task=25):
 
 # ---- clocks -------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region.  NVML is polled from a thread every
+    few milliseconds (a timed region at N=8 lasts ~65 ms, too short for `nvidia-smi -lms`); nvidia-smi is
+    the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
+        self.p = self.f = self.thread = None
+        self.samples = []
+        try:
+            import threading
+
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((sm, pw, int(rs)))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.004)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
@@ -136,6 +176,19 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                sm = sorted(x[0] for x in self.samples)
+                reasons = set()
+                for _, _, rs in self.samples:
+                    for bit, nme in self.NVML_REASONS.items():
+                        if rs & bit:
+                            reasons.add(nme)
+                out.update(sm_mhz=float(np.median(sm[len(sm) // 2:])), sm_max_mhz=self.mx, reasons=sorted(reasons),
+                           samples=len(sm), power_w_max=float(max(x[1] for x in self.samples)), source="nvml")
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -163,7 +216,7 @@ class ClockSampler:
         if sm:
             hi = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
             out.update(sm_mhz=float(np.median(hi)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(pw)))
+                       samples=len(sm), power_w_max=float(max(pw)), source="nvidia-smi")
         return out
 
 
