@@ -478,7 +478,7 @@ extern "C" int ssfe_extract(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_de
 }
 
 // Host buffers in and out.  The batch is cut into sub-batches (host_chunk_samples, 256 M samples by
-// default, ramping up at the start and down at the end) that flow through the PCM upload stream, two
+// default, ramping up from 1/8 at the start and down to 1/4 at the end) that flow through the PCM upload stream, two
 // compute lanes and the download stream: H2D of later sub-batches, the kernels of two sub-batches and
 // D2H of an earlier one overlap; input and output slots are four deep.  Every lane generates the
 // dither of its own sub-batches (jump-ahead makes any stream position cheap, mt19937.cu).
@@ -502,27 +502,31 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     const int64_t kChunkSamples = ctx->host_chunk_samples;
     std::vector<int64_t> targets;
     {
+        // ramp up (T/8, T/8, T/4, T/4, T/2, T/2), full sub-batches, ramp down (T/2, T/4); a remainder too
+        // small to stand alone is merged into the first ramp-down sub-batch
         int64_t remaining = b->sample_offsets[n] - b->sample_offsets[0];
-        const int64_t q = std::max<int64_t>(kChunkSamples / 4, 1), tail_sum = 3 * q;
-        const bool ramp = !getenv("SSFE_HOST_NORAMP");
-        for (int64_t h : {q, 2 * q})
-            if (ramp && remaining > tail_sum + h) {
-                targets.push_back(h);
-                remaining -= h;
+        const int64_t T = std::max<int64_t>(kChunkSamples, 8), down_sum = T / 2 + T / 4;
+        if (remaining <= T / 4) {
+            targets.push_back(remaining);
+        } else if (remaining <= down_sum + T / 8) {
+            targets.push_back(remaining / 3);
+            targets.push_back(remaining / 3);
+            targets.push_back(remaining - 2 * (remaining / 3));
+        } else {
+            for (int64_t h : {T / 8, T / 8, T / 4, T / 4, T / 2, T / 2})
+                if (remaining - h >= down_sum) {
+                    targets.push_back(h);
+                    remaining -= h;
+                }
+            while (remaining - T >= down_sum) {
+                targets.push_back(T);
+                remaining -= T;
             }
-        while (remaining > tail_sum + kChunkSamples) {
-            targets.push_back(kChunkSamples);
-            remaining -= kChunkSamples;
+            const int64_t rest = remaining - down_sum;          // 0 <= rest < T
+            if (rest >= T / 4) targets.push_back(rest);
+            targets.push_back(T / 2 + (rest < T / 4 ? rest : 0));
+            targets.push_back(T / 4);
         }
-        if (ramp && remaining > tail_sum) {
-            targets.push_back(remaining - tail_sum);
-            remaining = tail_sum;
-        }
-        if (ramp && remaining > q) {
-            targets.push_back(remaining - q);
-            remaining = q;
-        }
-        targets.push_back(remaining);
     }
     std::vector<int> cuts{0};
     {
