@@ -227,13 +227,15 @@ __device__ __forceinline__ float warp_max(float v)
 }
 
 // peaks of correl[0..nl) above cand_thresh*maxval, in ascending lag order (get_cand)
+// [i_lo, i_hi): the index range that can hold non-zero correlations (everything outside is zero and,
+// with clip >= 0, can never be a peak), so the scan may skip it
 __device__ __forceinline__ int pick_candidates(const float *cc, int nl, int firstlag, float maxval,
-                                               float *peaks, int *locs, int lane)
+                                               float *peaks, int *locs, int lane, int i_lo = 1, int i_hi = 1 << 30)
 {
     const float clip = c_rapt.cand_thresh * maxval;
-    const int lastl = nl - 2;
+    const int lastl = min(nl - 2, i_hi);
     int count = 0;
-    for (int base = 1; base < lastl; base += 32) {
+    for (int base = max(1, i_lo); base < lastl; base += 32) {
         const int i = base + lane;
         bool ok = false;
         float q = 0.0f;
@@ -461,6 +463,18 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
         }
         engr = __shfl_sync(0xffffffffu, s2, 31);
         maxval = 0.0f;
+        // The fine correlation is non-zero only inside the 7-lag windows, so only the span of those
+        // windows (plus one zero on either side, which the peak test reads) is cleared and scanned.
+        int z_lo = 0, z_hi = 0;
+        {
+            int mn = (lane < ncand) ? my_st : (1 << 30), mx = (lane < ncand) ? my_st : -(1 << 30);
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (ncand > 0) {
+                z_lo = max(mn - start0 - 1, 0);
+                z_hi = min(mx - start0 + 7 + 1, nlags0);
+            }
+        }
         if (engr > 0.0f) {
             float vmax = 0.0f;
             // cross products, one left-to-right chain per (candidate, lag).  With more than 32 chains a
@@ -518,7 +532,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
                 vmax = fmaxf(vmax, v);
             }
             __syncwarp();
-            for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;      // (the energies lived here)
+            for (int t = z_lo + lane; t < z_hi; t += 32) cc[t] = 0.0f;      // (the energies lived here)
             __syncwarp();
             // windows are written in candidate order; later ones overwrite earlier ones
             for (int c = 0; c < ncand; ++c) {
@@ -527,11 +541,9 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
                 __syncwarp();
             }
             maxval = warp_max(vmax);       // max over every value computed (order independent)
-        } else {
-            for (int t = lane; t < nlags0; t += 32) cc[t] = 0.0f;
         }
         __syncwarp();
-        ncand = pick_candidates(cc, nlags0, start0, maxval, pk, lc, lane);
+        ncand = (engr > 0.0f) ? pick_candidates(cc, nlags0, start0, maxval, pk, lc, lane, z_lo + 1, z_hi - 1) : 0;
         ncand = prune_candidates(pk, lc, ncand, lane);
 
         // local costs (A5) and the value each candidate would emit (A8)
