@@ -283,7 +283,7 @@ constexpr int kCandWarps = 4;
 
 constexpr int kCandTile = 16;      // frames per CTA (one binary search per tile, 4 frames per warp)
 
-__global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off,
+__global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off,
                                                                     const int *__restrict__ tile_map)
 {
     __shared__ __align__(16) float s_db[kCandWarps][448];
@@ -292,109 +292,140 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
     __shared__ __align__(16) float s_pklc[kCandWarps][2 * kPkMax];  // peaks | lags; between prune and pick: fine squares
     __shared__ int s_st[kCandWarps][kCMax];
 
-    __shared__ double s_sq[kCandWarps][64];      // squares of the coarse window, as doubles
-    __shared__ double s_ec[kCandWarps][40];      // lagged energy per coarse lag
+    // candidates of the warp's four frames after the coarse stage: [4][20] peaks, [4][20] lags, [4] counts
+    __shared__ __align__(16) float s_stash[kCandWarps][4 * kCMax + 4 * kCMax + 4];
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float *db = s_db[w], *cc = s_cc[w], *val = s_val[w], *pk = s_pklc[w];
     int *lc = reinterpret_cast<int *>(s_pklc[w] + kPkMax), *stc = s_st[w];
     float *sqf = s_pklc[w];                        // [448] squares of the mean-free fine window
     double *ecf = reinterpret_cast<double *>(s_cc[w]);   // [7 * ncand] lagged energy of every (candidate, lag)
-    double *sq = s_sq[w], *ec = s_ec[w];
 
     const int u = tile_map[blockIdx.x];
     const RaptUtt ut = p.utts[u];
     const RaptCfg &cf = c_rapt.cfg[ut.cfg];
     const int g_tile = (static_cast<int>(blockIdx.x) - tile_off[u]) * kCandTile;
-  for (int fk = w; fk < kCandTile; fk += kCandWarps) {
-    const int g = g_tile + fk;
-    if (g >= ut.n_fr) break;
-    const long long gf = ut.fr_off + g;
-    int r, i, nfr_r;
-    const int full = ut.R_last * cf.F;
-    if (g < full) { r = g / cf.F; i = g - r * cf.F; nfr_r = cf.F; }
-    else { r = ut.R_last; i = g - full; nfr_r = ut.nl; }
-    const bool flushed = (r == ut.R_last) && (r > 0);     // last read of several: the FIR was flushed
-    const int samsds = ((nfr_r - 1) * kHop + cf.ncomp) / kDec;
     const float *x = p.wav + ut.wav_off;
-    const float *ds = p.ds + ut.ds_off + static_cast<long long>(r) * (cf.sdstep / kDec);
+    float *st_pk = s_stash[w];
+    int *st_lc = reinterpret_cast<int *>(s_stash[w] + 4 * kCMax), *st_n = reinterpret_cast<int *>(s_stash[w] + 8 * kCMax);
 
-    // -- coarse stage on the 2 kHz stream ---------------------------------------------------------
-    for (int t = lane; t < cf.n_el; t += 32) {
-        const int q = (kHop / kDec) * i + t;
-        float v = 0.0f;
-        if (q < samsds) {
-            v = ds[q];
-        } else if (flushed) {
-            // samples the original produced while flushing the filter with zeros: output e of the
-            // flush sees its last 8e taps zeroed
-            const int e = q - samsds;
-            if (e == 0) {
-                v = ds[q];
-            } else {
-                const int base = r * cf.sdstep + kDec * q - (kNco / 2);
-                float sum = 0.0f;
-                for (int j = 0; j < kNco - kDec * e; ++j) {
-                    const int idx = base + j;
-                    const float xv = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
-                    sum += c_rapt.co[j] * xv;
-                }
-                v = static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
-            }
-        }
-        db[t] = v;
-    }
-    __syncwarp();
-    float maxval = 0.0f;
-    int ncand = 0;
+    // -- coarse stage on the 2 kHz stream, the warp's FOUR frames at once ----------------------------
+    // A quarter-warp per frame (frame w + 4 q for lanes 8 q .. 8 q + 7).  The coarse window is only ~57
+    // samples and its expensive parts are short sequential chains (mean, energies, the lagged-energy
+    // update) that one lane has to walk: with a whole warp per frame they ran on 1 lane of 32, here four
+    // frames' chains advance together.  Control flow is uniform across the warp (same configuration for
+    // all frames of an utterance), validity is a predicate, so every __syncwarp / ballot is convergent.
+    // The working buffers alias the fine-stage arrays, which are idle until the loop below.
     {
+        const int sub = lane >> 3, l8 = lane & 7;
+        const int gq = g_tile + w + kCandWarps * sub;
+        const int gc = min(gq, ut.n_fr - 1);                       // frames past the end: computed, not kept
+        float *cdb = s_cc[w] + 64 * sub;                           // [64] coarse window
+        double *cec = reinterpret_cast<double *>(s_db[w]) + 40 * sub;   // [40] lagged energy per lag
+        float *ccc = s_pklc[w] + 40 * sub;                         // [40] coarse correlation
+        float *cpk = s_pklc[w] + 160 + kCMax * sub;                // [20] peaks
+        int *clc = reinterpret_cast<int *>(s_pklc[w] + 160 + 4 * kCMax) + kCMax * sub;   // [20] lags
+        int r, i, nfr_r;
+        const int full = ut.R_last * cf.F;
+        if (gc < full) { r = gc / cf.F; i = gc - r * cf.F; nfr_r = cf.F; }
+        else { r = ut.R_last; i = gc - full; nfr_r = ut.nl; }
+        const bool flushed = (r == ut.R_last) && (r > 0);     // last read of several: the FIR was flushed
+        const int samsds = ((nfr_r - 1) * kHop + cf.ncomp) / kDec;
+        const float *ds = p.ds + ut.ds_off + static_cast<long long>(r) * (cf.sdstep / kDec);
+        for (int t = l8; t < cf.n_el; t += 8) {
+            const int q = (kHop / kDec) * i + t;
+            float v = 0.0f;
+            if (q < samsds) {
+                v = ds[q];
+            } else if (flushed) {
+                // samples the original produced while flushing the filter with zeros: output e of the
+                // flush sees its last 8e taps zeroed
+                const int e = q - samsds;
+                if (e == 0) {
+                    v = ds[q];
+                } else {
+                    const int base = r * cf.sdstep + kDec * q - (kNco / 2);
+                    float sum = 0.0f;
+                    for (int j = 0; j < kNco - kDec * e; ++j) {
+                        const int idx = base + j;
+                        const float xv = (idx >= 0 && idx < ut.L) ? x[idx] * 32768.0f : 0.0f;
+                        sum += c_rapt.co[j] * xv;
+                    }
+                    v = static_cast<float>((sum < 0.0) ? static_cast<double>(sum) - 0.5 : static_cast<double>(sum) + 0.5);
+                }
+            }
+            cdb[t] = v;
+        }
+        __syncwarp();
         const int size = cf.decsize, start = cf.decstart, nlags = cf.decnlags;
         float engr = 0.0f;
-        for (int j = 0; j < size; ++j) engr += db[j];
+        for (int j = 0; j < size; ++j) engr += cdb[j];
         engr /= size;
         __syncwarp();
-        for (int t = lane; t < cf.n_el; t += 32) db[t] = db[t] - engr;
+        for (int t = l8; t < cf.n_el; t += 8) cdb[t] = cdb[t] - engr;
         __syncwarp();
         float sum = 0.0f;
-        for (int j = 0; j < size; ++j) { const float st = db[j]; sum += st * st; }
+        for (int j = 0; j < size; ++j) { const float st = cdb[j]; sum += st * st; }
         engr = sum;
-        float t0 = 0.0f, t1 = 0.0f;
-        if (engr > 0.0f) {
-            sum = 0.0f;
-            for (int j = 0; j < size; ++j) { const float st = db[start + j]; sum += st * st; }
-            double engc = sum;
-            float dot0 = 0.0f, dot1 = 0.0f;
-            if (lane < nlags)
-                for (int j = 0; j < size; ++j) dot0 += db[j] * db[lane + start + j];
-            if (lane + 32 < nlags)
-                for (int j = 0; j < size; ++j) dot1 += db[j] * db[lane + 32 + start + j];
-            // The lagged energy is a running (sequential, double) update.  The squares it adds and
-            // removes are formed once, in parallel (float product, then widened - as the original
-            // does); the chain itself is two double adds and a clamp per lag, and its values are
-            // published through shared memory so that the square root and the division - the
-            // expensive part - are done once per lag, by the lane that owns it.
-            for (int t = lane; t < cf.n_el; t += 32) sq[t] = static_cast<double>(db[t] * db[t]);
-            __syncwarp();
-            if (lane == 0) {
-                for (int k = 0; k < nlags; ++k) {
-                    ec[k] = engc;
-                    engc -= sq[k + start];
-                    if ((engc += sq[k + start + size]) < 1.0) engc = 1.0;
-                }
-            }
-            __syncwarp();
-            if (lane < nlags) t0 = dot0 / sqrt(ec[lane] * engr);
-            if (lane + 32 < nlags) t1 = dot1 / sqrt(ec[lane + 32] * engr);
+        const bool pos_e = engr > 0.0f;
+        sum = 0.0f;
+        for (int j = 0; j < size; ++j) { const float st = cdb[start + j]; sum += st * st; }
+        // cross products, one left-to-right chain per lag
+        for (int lag = l8; lag < nlags; lag += 8) {
+            float dot = 0.0f;
+            for (int j = 0; j < size; ++j) dot += cdb[j] * cdb[lag + start + j];
+            ccc[lag] = dot;
         }
-        if (lane < nlags) cc[lane] = t0;
-        if (lane + 32 < nlags) cc[lane + 32] = t1;
-        maxval = warp_max(fmaxf(fmaxf(t0, t1), 0.0f));
+        // the lagged energy is a running (sequential, double) update: one lane per frame walks it and
+        // publishes the values, so that the square root and the division are done by the lane that owns a lag
+        if (l8 == 0) {
+            double engc = sum;
+            for (int k = 0; k < nlags; ++k) {
+                cec[k] = engc;
+                const float a0 = cdb[k + start], az = cdb[k + start + size];
+                engc -= static_cast<double>(a0 * a0);
+                if ((engc += static_cast<double>(az * az)) < 1.0) engc = 1.0;
+            }
+        }
         __syncwarp();
-        ncand = pick_candidates(cc, nlags, start, maxval, pk, lc, lane);
+        float tmax = 0.0f;
+        for (int lag = l8; lag < nlags; lag += 8) {
+            const float t = pos_e ? static_cast<float>(ccc[lag] / sqrt(cec[lag] * engr)) : 0.0f;
+            ccc[lag] = t;
+            tmax = fmaxf(tmax, t);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        const float maxval_c = tmax;
+        __syncwarp();
+        // peaks above cand_thresh * maxval, in ascending lag order (get_cand), eight lags per step
+        int ncand_c = 0;
+        {
+            const float clip = c_rapt.cand_thresh * maxval_c;
+            const int lastl = nlags - 2;
+            for (int base = 1; base < lastl; base += 8) {
+                const int ii = base + l8;
+                bool ok = false;
+                float q = 0.0f;
+                if (ii < lastl) {
+                    q = ccc[ii];
+                    ok = (q > clip) && (q >= ccc[ii + 1]) && (q >= ccc[ii - 1]);
+                }
+                const unsigned m8 = (__ballot_sync(0xffffffffu, ok) >> (8 * sub)) & 0xffu;
+                const int pos = ncand_c + __popc(m8 & ((1u << l8) - 1u));
+                if (ok && pos < kCMax) {
+                    cpk[pos] = q;
+                    clc[pos] = ii + start;
+                }
+                ncand_c += __popc(m8);
+            }
+            ncand_c = min(ncand_c, kCMax);
+        }
+        __syncwarp();
         // parabolic refinement to full-rate lags
         const float lag_wt = cf.lag_wt;
-        for (int c = lane; c < ncand; c += 32) {
-            const float *y = cc + (lc[c] - start - 1);
+        for (int c = l8; c < ncand_c; c += 8) {
+            const float *y = ccc + (clc[c] - start - 1);
             float xp, yp;
             const float a = static_cast<float>((y[2] - y[1]) + (.5 * (y[0] - y[2])));
             if (fabs(a) > .000001) {
@@ -405,13 +436,50 @@ __global__ void __launch_bounds__(kCandWarps * 32) rapt_cand_kernel(const RaptPa
                 xp = 0.0f;
                 yp = y[1];
             }
-            const int l2 = (lc[c] * kDec) + static_cast<int>(0.5 + (xp * kDec));
-            lc[c] = l2;
-            pk[c] = yp * (1.0 - (lag_wt * l2));
+            const int l2 = (clc[c] * kDec) + static_cast<int>(0.5 + (xp * kDec));
+            clc[c] = l2;
+            cpk[c] = yp * (1.0 - (lag_wt * l2));
         }
         __syncwarp();
-        ncand = prune_candidates(pk, lc, ncand, lane);
+        // keep the n_cands - 1 largest (never needed for <= 40 coarse lags, kept for completeness)
+        if (ncand_c >= kCMax) {
+            if (l8 == 0) {
+                for (int outer = 0; outer < kCMax - 1; ++outer) {
+                    int idx = ncand_c - 1;
+                    for (int inner = ncand_c - 1 - outer; inner-- > 0; --idx) {
+                        const float sm = cpk[idx];
+                        if (sm > cpk[idx - 1]) {
+                            const int lt = clc[idx];
+                            cpk[idx] = cpk[idx - 1];
+                            cpk[idx - 1] = sm;
+                            clc[idx] = clc[idx - 1];
+                            clc[idx - 1] = lt;
+                        }
+                    }
+                }
+            }
+            ncand_c = kCMax - 1;
+        }
+        __syncwarp();
+        for (int c = l8; c < ncand_c; c += 8) {
+            st_pk[kCMax * sub + c] = cpk[c];
+            st_lc[kCMax * sub + c] = clc[c];
+        }
+        if (l8 == 0) st_n[sub] = ncand_c;
+        __syncwarp();
     }
+
+  for (int fq = 0; fq < kCandTile / kCandWarps; ++fq) {
+    const int g = g_tile + w + kCandWarps * fq;
+    if (g >= ut.n_fr) break;
+    const long long gf = ut.fr_off + g;
+    float maxval = 0.0f;
+    int ncand = st_n[fq];
+    if (lane < ncand) {
+        pk[lane] = st_pk[kCMax * fq + lane];
+        lc[lane] = st_lc[kCMax * fq + lane];
+    }
+    __syncwarp();
 
     // -- fine stage on the full-rate signal ---------------------------------------------------------
     {
