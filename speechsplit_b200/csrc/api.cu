@@ -287,10 +287,11 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
         for (cudaEvent_t e : row)
             if (e) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
-    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1], ctx->ev_h2d[0],
-                          ctx->ev_h2d[1], ctx->ev_h2d[2], ctx->ev_h2d[3], ctx->ev_comp[0], ctx->ev_comp[1], ctx->ev_comp[2], ctx->ev_comp[3],
-                          ctx->ev_d2h[0], ctx->ev_d2h[1], ctx->ev_d2h[2], ctx->ev_d2h[3]})
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1]})
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < ssfe_ctx::kHostSlots; ++i)
+        for (cudaEvent_t e : {ctx->ev_h2d[i], ctx->ev_comp[i], ctx->ev_d2h[i]})
+            if (e) cudaEventDestroy(e);
     for (auto &row : ctx->ev_auxr)
         for (cudaEvent_t e : row)
             if (e) cudaEventDestroy(e);
@@ -558,7 +559,7 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     // Two compute lanes (full contexts of their own: stream, side stream, workspace) take the
     // sub-batches alternately, so that the serial chains inside a sub-batch (filter carries, Viterbi,
     // the tails of 20 kernels) are covered by the other lane's kernels instead of idling the GPU.
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < ssfe_ctx::kHostLanes; ++i)
         if (!ctx->lane[i]) {
             if ((rc = ssfe_create(&ctx->lane[i], ctx->device, &ctx->cfg)))
                 return set_error(ctx, rc, "ssfe_extract_host: lane context: %s", ssfe_last_error(nullptr));
@@ -578,7 +579,7 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
     SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_fork, 0));
-    for (int i = 0; i < 2; ++i) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[i]->stream, ctx->ev_fork, 0));
+    for (int i = 0; i < ssfe_ctx::kHostLanes; ++i) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[i]->stream, ctx->ev_fork, 0));
 
     const bool trace = getenv("SSFE_TRACE_HOST") != nullptr;
     std::vector<cudaEvent_t> tev;
@@ -593,7 +594,7 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     const char *src = static_cast<const char *>(x_host);
     for (int c = 0; c < n_chunks; ++c) {
         const int u0 = cuts[c], u1 = cuts[c + 1], m = u1 - u0, slot = c % n_slots;
-        ssfe_ctx *ln = ctx->lane[c & 1];
+        ssfe_ctx *ln = ctx->lane[c % ssfe_ctx::kHostLanes];
         char *base = static_cast<char *>(ctx->h_x.p) + slot * slot_b;
         void *d_x = base;
         float *d_mel = reinterpret_cast<float *>(base + in_b);
@@ -646,7 +647,7 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         tmark(ctx->copy_out);
     }
     SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));      // every sub-batch's results are on the host
-    for (int i = 0; i < 2; ++i) SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->lane[i]->stream));
+    for (int i = 0; i < ssfe_ctx::kHostLanes; ++i) SSFE_CUDA(ctx, cudaStreamSynchronize(ctx->lane[i]->stream));
     if (trace) {
         for (int c = 0; c < n_chunks; ++c) {
             float a, b2, cc, d;

@@ -53,7 +53,8 @@ struct ssfe_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     static constexpr int kHostSlots = 4;                      // device slots of ssfe_extract_host
     cudaEvent_t ev_h2d[kHostSlots] = {}, ev_comp[kHostSlots] = {}, ev_d2h[kHostSlots] = {};
-    ssfe_ctx *lane[2] = {nullptr, nullptr};                   // compute lanes of ssfe_extract_host (created on first use)
+    static constexpr int kHostLanes = 2;                      // compute lanes of ssfe_extract_host
+    ssfe_ctx *lane[kHostLanes] = {};                          // (full contexts, created on first use)
     cudaEvent_t ev_dith_free = nullptr;                       // recorded after the kernel that reads `dith`
     cudaEvent_t ev_mt_go = nullptr;                           // recorded where the NEXT call's dither walk may start
     char *aux_host[2] = {nullptr, nullptr}, *aux_dev[2] = {nullptr, nullptr};   // side-stream metadata staging

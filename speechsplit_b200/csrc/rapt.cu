@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const Rap
         float s2 = 0.0f;
         if (lane < ncand || lane == 31) {
             const float *q = sqf + my_st;
-#pragma unroll 8
+#pragma unroll 20
             for (int j = 0; j < kWin; ++j) s2 += q[j];
         }
         engr = __shfl_sync(0xffffffffu, s2, 31);
