@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32, 4) filt_tile_kernel(const Fil
     const double *dith = (FINAL && PASS == 1 && p.dith) ? p.dith + fbase : nullptr;
     float *wavp = (FINAL && PASS == 1 && p.wavp) ? p.wavp + p.seg_off[u] + kHalfPad : nullptr;
     // ---- load machinery -------------------------------------------------------------------------------
+    // (For 16-bit input a tile is one contiguous 16 KB run; fetching it with a single TMA bulk copy into
+    // shared memory and cutting the sub-tiles from there was built and measured: correct, but the 16.5 KB
+    // of staging per warp leave 8 warps per SM instead of 16 and the forward passes took 5 ms LONGER.)
     // The kernel is bound by global-memory latency.  (1) On the common path (full tile, every row
     // segment inside the signal) the 32 raw values of a sub-tile are fetched branch-free into registers
     // and only later converted and stored - a conversion placed right behind its load makes the
