@@ -198,7 +198,7 @@ template <> struct RawType<SSFE_I16, 0> { using T = short; };
 template <> struct RawType<SSFE_F32, 0> { using T = float; };
 
 template <int DTYPE, int PASS, bool FINAL>
-__global__ void __launch_bounds__(kFiltWarps * 32, 4) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
+__global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
                                                                      int n_tiles, const int *__restrict__ tile_map)
 {
     __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
