@@ -33,10 +33,11 @@ extern "C" void ssfe_filt_power_table_dd(const double *a6, int base, int count, 
 constexpr int kChunk = 256;
 constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
 constexpr int kFiltThreads = 128;
-// Utterances of at least this many chunks (>= 4.1 s) take the warp-parallel carry, shorter ones the
-// thread-per-utterance carry: the scan does 7x the arithmetic, which only pays when the chain is long.
+// Utterances of at least this many chunks (>= 16.4 s) take the warp-parallel carry, shorter ones the
+// five-lanes-per-utterance carry: the scan does 7x the arithmetic, which only pays when the chain is
+// long (a 500-chunk utterance takes ~56 us in the lane-group kernel, 160 us in the scan).
 // The rule depends on the utterance alone, never on the batch, so results stay batch independent.
-constexpr int kWarpCarryMin = 256;
+constexpr int kWarpCarryMin = 1024;
 
 
 struct FiltConsts {
