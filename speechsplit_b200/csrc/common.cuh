@@ -183,7 +183,7 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
 
 // launch_on: nullptr / ctx->stream = public path (doubles out); ctx->aux = side stream, raw word pairs
 // out, ordering handled inside (waits for ev_dith_free and ev_mt_go: starts beside the previous call's
-// Viterbi kernel).
+// stationarity kernel).
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
              int n, double *u_dev, cudaStream_t launch_on = nullptr);
 

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(kCarryThreads) filt_carry_kernel(const FiltPar
 }
 
 // ---- warp-parallel carry ----------------------------------------------------------------------------
-// The thread-per-utterance carry above is one latency chain of (chunks) double-double mat-vecs: 188 for
+// The lane-group carry above is one latency chain of (chunks) double-double mat-vecs: 188 for
 // a 3 s utterance, 3751 for a 60 s one (26 ms per pass).  Here a WARP owns an utterance: lane = chunk
 // inside a tile of 32, and the recurrence z[c+1] = M z[c] + s[c] (M = A^256) is solved per tile by a
 // Kogge-Stone scan over the lanes with the precomputed powers P[j] = M^j, j = 1..32 (double-double,
