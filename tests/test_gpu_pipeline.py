@@ -234,3 +234,75 @@ def test_make_spect_f0_script_drop_in(tmp_path):
             total += b.size
     assert worst <= 1e-4, worst
     assert same / total >= 0.999, (same, total)
+
+
+def test_extract_large_corpus_properties(fe):
+    """One GPU's share of the benchmark corpus at N=8 (14 speakers x 400 utterances, 16 800 audio-s,
+    ~1.05 M frames) through size-independent properties: results do not depend on batch order or on how
+    the corpus is split over calls (bitwise), the device and the host entry points agree, frame counts
+    follow make_spect_f0.py:69, every one-hot row has exactly one 1 at its bin, and a sample of
+    utterances matches the oracle within the north_star tolerances."""
+    from speechsplit_b200.sharding import dither_skips
+    metas = make_manifest(14, 400, seed=0)
+    pcm = synth_batch(metas, device="cuda")
+    lens = np.array([m.length for m in metas])
+    skips = dither_skips([m.spk for m in metas], lens)
+    lo = np.array([50.0 if m.gender == "M" else 100.0 for m in metas], np.float32)
+    hi = np.array([250.0 if m.gender == "M" else 600.0 for m in metas], np.float32)
+    seed = np.array([m.spk_id for m in metas], np.uint32)
+
+    def run(idx, want=("mel", "f0_norm", "bins")):
+        off = np.concatenate([[0], np.cumsum(lens[idx])]).astype(np.int64)
+        x = torch.cat([pcm[i] for i in idx])
+        return fe.extract(x, off, lo[idx], hi[idx], seed[idx], skips[idx], want=want)
+
+    n = len(metas)
+    whole = run(np.arange(n), want=("mel", "f0_norm", "bins", "onehot"))
+    fo = whole["frame_offsets"]
+    fixed = lens + (lens % 256 == 0)                                  # make_spect_f0.py:52-53
+    assert np.array_equal(np.diff(fo), -(-fixed // 256))                # T = ceil(L' / 256) = len(f0_rapt), :69
+    assert (lens % 256 == 0).sum() >= 80                               # the append path is exercised
+    bins = whole["bins"]
+    assert int(bins.min()) >= 0 and int(bins.max()) <= 256
+    onehot = whole["onehot"]
+    assert torch.equal(onehot.argmax(1), bins) and bool((onehot.sum(1) == 1).all())
+    voiced = float((bins > 0).float().mean())
+    assert 0.2 < voiced < 0.95, voiced
+
+    # a permutation, processed as three separate calls, must reproduce every utterance bit for bit
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(n)
+    pos = 0
+    for part in np.array_split(perm, 3):
+        res = run(part)
+        pfo = res["frame_offsets"]
+        for k in rng.choice(len(part), 40, replace=False):
+            i = part[k]
+            assert torch.equal(res["mel"][pfo[k]:pfo[k + 1]], whole["mel"][fo[i]:fo[i + 1]]), i
+            assert torch.equal(res["bins"][pfo[k]:pfo[k + 1]], whole["bins"][fo[i]:fo[i + 1]]), i
+        pos += len(part)
+
+    # host entry point == device entry point
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    host = fe.extract_host(torch.cat(pcm).cpu(), off, lo, hi, seed, skips)
+    assert np.array_equal(host["mel"], whole["mel"].cpu().numpy())
+    assert np.array_equal(host["bins"], whole["bins"].cpu().numpy())
+
+    # a sample against the oracle (each with its speaker's stream advanced to the utterance)
+    worst, same, total = 0.0, 0, 0
+    for i in (0, 399, 400, 2801, 5599):
+        m = metas[i]
+        prng = RandomState(m.spk_id)
+        left = int(skips[i])
+        while left:
+            step = min(left, 10_000_000)
+            prng.rand(step)
+            left -= step
+        S, f0n = rp.extract_utterance(pcm_to_float64(pcm[i].cpu().numpy()), m.gender, prng)
+        worst = max(worst, float(np.abs(whole["mel"][fo[i]:fo[i + 1]].cpu().numpy() - S).max()))
+        b_ref = rp.quantize_f0_numpy(f0n.astype(np.float32))[1]
+        b = whole["bins"][fo[i]:fo[i + 1]].cpu().numpy()
+        same += int((b == b_ref).sum())
+        total += b.size
+    assert worst <= 1e-4, worst
+    assert same >= 0.999 * total, (same, total)
