@@ -224,7 +224,7 @@ class ClockSampler:
 def build_shard(args, rank, world):
     """Manifest -> LPT shard of this rank -> control tracks (process pool, before CUDA is touched)."""
     from speechsplit_b200.corpus import control_tracks, make_manifest
-    from speechsplit_b200.sharding import dither_skips, lpt_shards_by_speaker
+    from speechsplit_b200.sharding import contiguous_shards, dither_skips
     if args.workload == "longform":       # configs[3]: 4 speakers x 64 utterances of 60.000 s
         metas = make_manifest(4, 64, seed=0, fixed_len=960000)
     elif args.workload == "single":       # configs[0]: one 3 s male utterance (p226)
@@ -232,7 +232,7 @@ def build_shard(args, rank, world):
     else:
         metas = make_manifest(args.speakers, args.utts, seed=0)
     skips = dither_skips([m.spk for m in metas], [m.length for m in metas])
-    shard = lpt_shards_by_speaker([m.spk for m in metas], [m.length for m in metas], world)[rank]
+    shard = contiguous_shards([m.length for m in metas], world)[rank]
     mine = [metas[i] for i in shard]
     tracks = get_pool().map(control_tracks, mine, chunksize=64)
     return metas, mine, skips[shard], tracks
@@ -438,7 +438,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (STFT/mel), f64 (filtfilt), f32+f64 (RAPT)",
             "data": "synthetic",
             "config": {"workload": "VCTK-shaped synthetic corpus: %d speakers x %d utterances, %.0f audio-s, 16 kHz int16 PCM "
-                                   "(BASELINE.json configs[1]); at N>1 the same corpus LPT-sharded, whole speakers per GPU (configs[2])"
+                                   "(BASELINE.json configs[1]); at N>1 the same corpus cut into N consecutive runs of equal sample count (configs[2])"
                                    % (args.speakers, args.utts, audio_s_total),
                        "utterances": len(metas), "frames": int(T) if world == 1 else None,
                        "outputs": "mel f32 [T,80], f0_norm f32 [T], bins i64 [T], one-hot f32 [T,257]",

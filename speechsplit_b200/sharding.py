@@ -62,3 +62,28 @@ def lpt_shards_by_speaker(speakers: Sequence[str], lengths: Sequence[int], n_sha
         load[j] += totals[k]
     owner = owner_of_spk[inv]
     return [np.nonzero(owner == k)[0] for k in range(n_shards)]
+
+
+def contiguous_shards(lengths: Sequence[int], n_shards: int) -> List[np.ndarray]:
+    """Cut the corpus, in its own order (speakers sorted, files sorted), into ``n_shards`` consecutive
+    runs of equal sample count.
+
+    With the jump-ahead generator (csrc/mt19937.cu) a shard may start anywhere in a speaker's dither
+    stream for the price of one segment start, so speakers no longer have to stay whole: every shard holds
+    whole speakers plus at most two partial ones, each partial speaker's files are one consecutive stretch
+    of its stream, and the load is balanced to within one utterance (the speaker-atomic split of 109
+    speakers over 8 GPUs was off by 2.8 %)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = len(lengths)
+    ends = np.cumsum(lengths)
+    total = int(ends[-1]) if n else 0
+    cuts = [0]
+    for k in range(1, n_shards):
+        target = total * k / n_shards
+        i = int(np.searchsorted(ends, target))              # first utterance whose end reaches the target
+        # cut before or after utterance i, whichever is closer to the target
+        before = int(ends[i - 1]) if i > 0 else 0
+        cut = i if (target - before) <= (int(ends[min(i, n - 1)]) - target) else i + 1
+        cuts.append(min(max(cut, cuts[-1]), n))
+    cuts.append(n)
+    return [np.arange(cuts[k], cuts[k + 1]) for k in range(n_shards)]

@@ -106,3 +106,27 @@ def test_two_rank_gloo_sharding(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_contiguous_shards_balance_and_stream_order():
+    """Consecutive runs of equal sample count: every utterance exactly once, corpus order kept (so each
+    shard's requests to a speaker's stream are one ascending stretch), load within one utterance of the
+    mean, at most two partial speakers per shard."""
+    from speechsplit_b200.corpus import make_manifest
+    from speechsplit_b200.sharding import contiguous_shards
+    metas = make_manifest(109, 40, seed=0)
+    lengths = np.array([m.length for m in metas])
+    spk = np.array([m.spk for m in metas])
+    for world in (1, 2, 3, 8):
+        shards = contiguous_shards(lengths, world)
+        assert len(shards) == world
+        allidx = np.concatenate(shards)
+        assert np.array_equal(allidx, np.arange(len(metas)))
+        loads = np.array([lengths[s].sum() for s in shards])
+        assert np.abs(loads - lengths.sum() / world).max() <= lengths.max()
+        for s in shards:
+            partial = [k for k in np.unique(spk[s]) if (spk[s] == k).sum() != (spk == k).sum()]
+            assert len(partial) <= 2
+    # degenerate: more shards than utterances
+    sh = contiguous_shards([5, 7], 4)
+    assert sorted(np.concatenate(sh).tolist()) == [0, 1] and len(sh) == 4
