@@ -69,13 +69,15 @@ void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
 {
     const size_t need = (bytes + 255) / 256 * 256;
     if (need > ctx->meta_cap) {
-        // grow: drain, then reallocate both halves
-        cudaStreamSynchronize(ctx->stream);
-        if (ctx->meta_host) cudaFreeHost(ctx->meta_host);
-        if (ctx->meta_dev) cudaFree(ctx->meta_dev);
+        // grow: the old arena may still hold metadata of kernels that are queued or not even launched yet
+        // (earlier uploads of the same call), so it is retired, not freed, until the context goes away
+        if (ctx->meta_host) ctx->retired_host.push_back(ctx->meta_host);
+        if (ctx->meta_dev) ctx->retired_dev.push_back(ctx->meta_dev);
         ctx->meta_host = nullptr;
         ctx->meta_dev = nullptr;
-        const size_t cap = std::max<size_t>(need * 4, 8u << 20);
+        // several calls' worth: the arena wraps (with a stream sync) only once every few calls, and a call's
+        // uploads (about 250 bytes per utterance in total, 56 in the largest single one) never lap themselves
+        const size_t cap = std::max<size_t>(need * 32, 64u << 20);
         if (cudaMallocHost(reinterpret_cast<void **>(&ctx->meta_host), cap) != cudaSuccess ||
             cudaMalloc(reinterpret_cast<void **>(&ctx->meta_dev), cap) != cudaSuccess) {
             set_error(ctx, SSFE_ERR_NOMEM, "metadata arena allocation of %zu bytes failed", cap);
@@ -281,6 +283,8 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     if (ctx->mt_taps) cudaFree(ctx->mt_taps);
     if (ctx->meta_host) cudaFreeHost(ctx->meta_host);
     if (ctx->meta_dev) cudaFree(ctx->meta_dev);
+    for (char *q : ctx->retired_host) cudaFreeHost(q);
+    for (char *q : ctx->retired_dev) cudaFree(q);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     for (auto &row : ctx->ev)

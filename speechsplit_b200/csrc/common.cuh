@@ -75,6 +75,7 @@ struct ssfe_ctx {
     char *meta_host = nullptr;
     char *meta_dev = nullptr;
     size_t meta_cap = 0, meta_used = 0;
+    std::vector<char *> retired_host, retired_dev;            // outgrown arenas, kept alive until destroy
     // tables
     float *d_window = nullptr;         // periodic Hann(1024)
     float2 *d_tw = nullptr;            // [k1][lane] = exp(-2 pi i lane k1 / 1024)
