@@ -8,6 +8,8 @@ Parity status:
   * stages a0-a3, a5, a7-a9 (filtfilt, dither, pySTFT, mel-dB, normalisation,
     quantisation): PINNED - the restatement is checked against the reference's own
     ``utils.py`` imported in the build container (tests/golden/make_golden.py).
+  * InterpLnr (oracle/interp_lnr.py): PINNED - bit-identical to the reference's own ``model.InterpLnr``
+    run in the build container on captured random draws (tests/golden/interp_lnr.npz).
   * stage a4 (librosa.filters.mel) and stage a6 (pysptk.sptk.rapt -> SPTK/Snack get_f0):
     PARITY UNPINNED - neither package (nor its source) exists in the build container, so
     these are restatements of the published algorithms, anchored on the reference's call
