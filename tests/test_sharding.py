@@ -75,7 +75,7 @@ import os, sys
 sys.path.insert(0, %(root)r)
 import numpy as np, torch, torch.distributed as dist
 from speechsplit_b200.corpus import make_manifest
-from speechsplit_b200.sharding import dither_skips, lpt_shards
+from speechsplit_b200.sharding import contiguous_shards, dither_skips, lpt_shards
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 metas = make_manifest(6, 10, seed=2)
@@ -89,6 +89,16 @@ t = torch.tensor([1.0 + rank], dtype=torch.float64)
 dist.barrier(); dist.all_reduce(t, op=dist.ReduceOp.MAX)     # bench.py: max over ranks
 assert t.item() == float(world)
 cnt = torch.tensor([len(shard)]); dist.all_reduce(cnt); assert cnt.item() == len(metas)
+# the split bench.py uses: consecutive runs of equal sample count, every rank computes the same cut
+cs = contiguous_shards(lengths, world)[rank]
+lo = torch.tensor([float(cs[0]) if len(cs) else 0.0, float(len(cs))], dtype=torch.float64)
+allr = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(allr, lo)
+starts = [int(a[0]) for a in allr]; counts = [int(a[1]) for a in allr]
+assert sum(counts) == len(metas) and all(starts[k] + counts[k] == starts[k + 1] for k in range(world - 1))
+load = torch.tensor([float(sum(lengths[i] for i in cs))], dtype=torch.float64)
+mx = load.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+assert mx.item() <= sum(lengths) / world + max(lengths)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok", len(shard), int(skips.sum()))
 """
