@@ -21,6 +21,7 @@
 //                      back-tracking at every 0.2 s read boundary, log(F0) output          (A7-A8)
 // K1-K3 are frame parallel (the bulk of the work); only K4 is sequential in time.
 #include "common.cuh"
+#include "tma.cuh"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -689,13 +690,16 @@ __device__ __forceinline__ void durbin18(const float *r, float *a_out, float *er
 // leaves room for only 5 warps per SM beside the 35 KB staged span, and the kernel took 21.9 ms.)
 // A CTA covers 32 consecutive frames of one utterance: warp 0 takes the current windows
 // (x + 256 g - 80), warp 1 the previous ones (x + 256 g - 400); the signal span is staged once
-// in shared memory (scaled by 32768, two pad words per 256 samples -> conflict-free 64-bit column reads).
+// in shared memory - for interior tiles by 35 TMA bulk copies of one 256-sample row each, issued by
+// one thread and awaited once (the element-wise staging it replaces exposed nine load round trips,
+// a fifth of the CTA's life); raw samples, the factor 32768 is folded exactly into the window tables.
+// Four pad words per 256 samples keep the rows 16-byte aligned for the copies.
 constexpr int kStatFrames = 32;
 constexpr int kStatSpan = kHop * (kStatFrames - 1) + kStatGap + kStatW;      // 16928 samples
 constexpr int kStatSpanPad = kStatSpan + 32;                                  // read-ahead of the last window
-constexpr int kStatXWords = kStatSpanPad + 2 * (kStatSpanPad / 256) + 2;
+constexpr int kStatXWords = kStatSpanPad + 4 * (kStatSpanPad / 256) + 4;
 constexpr int kStatWinPairs = 256;                                            // window pairs (zero past 479 / 480)
-__device__ __forceinline__ int stat_skew(int i) { return i + 2 * (i >> 8); }
+__device__ __forceinline__ int stat_skew(int i) { return i + 4 * (i >> 8); }
 
 __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptParams p, const int *__restrict__ tile_off,
                                                                     const int *__restrict__ tile_map)
@@ -711,29 +715,47 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
     const int g0 = (static_cast<int>(blockIdx.x) - tile_off[u]) * kStatFrames;
     const float *x = p.wav + ut.wav_off;
     const int s_lo = kHop * g0 - (kStatGap + 80);
-    for (int i0 = 0; i0 < kStatSpanPad; i0 += 16 * 2 * kStatFrames) {   // 16 loads in flight per thread
-        float raw[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int idx = s_lo + i0 + tid + q * 2 * kStatFrames;
-            raw[q] = x[min(max(idx, 0), ut.L - 1)];
+    __shared__ __align__(8) uint64_t s_bar;
+    // every staged sample is a sample of the utterance, and the run is 16-byte aligned (always true in the
+    // padded segment layout of ssfe_extract; the stage-level ssfe_rapt takes arbitrary offsets)
+    const bool interior = s_lo >= 0 && s_lo + kStatSpanPad <= ut.L && (reinterpret_cast<uintptr_t>(x + s_lo) & 15) == 0;
+    if (interior) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&s_bar, kStatSpanPad * 4);
+            constexpr int kRows = kStatSpanPad / 256, kRest = kStatSpanPad - 256 * kRows;
+            for (int k = 0; k < kRows; ++k) tma_load_1d(s_x + 260 * k, x + s_lo + 256 * k, 1024, &s_bar);
+            if (kRest) tma_load_1d(s_x + 260 * kRows, x + s_lo + 256 * kRows, kRest * 4, &s_bar);
         }
+    } else {
+        for (int i0 = 0; i0 < kStatSpanPad; i0 += 16 * 2 * kStatFrames) {   // 16 loads in flight per thread
+            float raw[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int i = i0 + tid + q * 2 * kStatFrames, idx = s_lo + i;
-            if (i < kStatSpanPad) s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? raw[q] * 32768.0f : 0.0f;
+            for (int q = 0; q < 16; ++q) {
+                const int idx = s_lo + i0 + tid + q * 2 * kStatFrames;
+                raw[q] = x[min(max(idx, 0), ut.L - 1)];
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int i = i0 + tid + q * 2 * kStatFrames, idx = s_lo + i;
+                if (i < kStatSpanPad) s_x[stat_skew(i)] = (idx >= 0 && idx < ut.L) ? raw[q] : 0.0f;
+            }
         }
     }
+    // window tables, times 32768: the original scales the samples, a power of two commutes with every
+    // rounding on the way, so scaling the weights instead gives the same bits
     for (int q = tid; q < kStatWinPairs; q += 2 * kStatFrames) {
         const int i = 2 * q;
         float4 w;
-        w.x = (i < kStatW) ? p.w480[i] : 0.0f;
-        w.y = (i + 1 < kStatW) ? p.w480[i + 1] : 0.0f;
-        w.z = (i < kStatW - 1) ? p.w479[i] : 0.0f;
-        w.w = (i + 1 < kStatW - 1) ? p.w479[i + 1] : 0.0f;
+        w.x = (i < kStatW) ? p.w480[i] * 32768.0f : 0.0f;
+        w.y = (i + 1 < kStatW) ? p.w480[i + 1] * 32768.0f : 0.0f;
+        w.z = (i < kStatW - 1) ? p.w479[i] * 32768.0f : 0.0f;
+        w.w = (i + 1 < kStatW - 1) ? p.w479[i + 1] * 32768.0f : 0.0f;
         s_w4[q] = w;
     }
     __syncthreads();
+    if (interior) mbar_wait(&s_bar, 0);
 
     const bool is_prev = tid >= kStatFrames;
     const int fl = is_prev ? tid - kStatFrames : tid;      // local frame
