@@ -7,7 +7,8 @@ not vendored in the reference and not installed here (README.md:28 lists it with
 version; the positional ``mel(sr, n_fft)`` call only works on librosa < 0.10).  This file
 restates the published algorithm of that version range: Slaney mel scale (htk=False),
 Slaney area normalisation (norm=1 / 'slaney'), float32 storage.
-Cross-check available in-container: torchaudio.functional.melscale_fbanks(...,'slaney','slaney').
+Cross-checks available in-container: torchaudio.functional.melscale_fbanks(...,'slaney','slaney') and
+transformers.audio_utils.mel_filter_bank(norm='slaney', mel_scale='slaney') (tests/test_oracle.py).
 """
 import numpy as np
 

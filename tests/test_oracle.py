@@ -75,6 +75,16 @@ def test_mel_basis_vs_torchaudio():
     assert np.abs(mel_filterbank() - t).max() < 2e-7
 
 
+def test_mel_basis_vs_transformers():
+    """Second independent restatement of librosa.filters.mel (transformers.audio_utils documents its
+    slaney/slaney filter bank as librosa's): same support, at most one f32 ulp apart."""
+    au = pytest.importorskip("transformers.audio_utils")
+    t = au.mel_filter_bank(513, 80, 90.0, 7600.0, 16000, norm="slaney", mel_scale="slaney").T.astype(np.float32)
+    w = mel_filterbank()
+    assert np.array_equal(w != 0, t != 0)
+    assert np.abs(w.view(np.int32) - t.view(np.int32)).max() <= 1
+
+
 @pytest.mark.parametrize("name", ["pipeline_p226.npz", "pipeline_p225.npz"])
 def test_pipeline_matches_reference(golden_dir, name):
     """make_spect_f0.py:47-74 through the oracle == through the reference's own functions."""
