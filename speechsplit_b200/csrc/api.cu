@@ -487,15 +487,16 @@ extern "C" int ssfe_extract(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_de
 // compute lanes and the download stream: H2D of later sub-batches, the kernels of two sub-batches and
 // D2H of an earlier one overlap; input and output slots are four deep.  Every lane generates the
 // dither of its own sub-batches (jump-ahead makes any stream position cheap, mt19937.cu).
-extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_host, int dtype, float *mel_host,
+static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_host, int dtype, float *mel_host,
                                  float *f0_norm_host, int64_t *bins_host)
 {
-    if (!ctx) return SSFE_ERR_INVALID;
     int rc = check_batch(ctx, b);
     if (rc) return rc;
     const int n = b->n_utts;
     if (n == 0) return SSFE_OK;
     if (!x_host || !mel_host || !f0_norm_host) return set_error(ctx, SSFE_ERR_INVALID, "ssfe_extract_host: null argument");
+    if (dtype != SSFE_F64 && dtype != SSFE_F32 && dtype != SSFE_I16)
+        return set_error(ctx, SSFE_ERR_INVALID, "ssfe_extract_host: unknown dtype %d", dtype);
     SSFE_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t esz = dtype == SSFE_F64 ? 8 : dtype == SSFE_F32 ? 4 : 2;
     std::vector<int64_t> fix(n + 1), foff(n + 1);
@@ -665,4 +666,20 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return SSFE_OK;
+}
+
+extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_host, int dtype, float *mel_host,
+                                 float *f0_norm_host, int64_t *bins_host)
+{
+    if (!ctx) return SSFE_ERR_INVALID;
+    const int rc = extract_host_pipeline(ctx, b, x_host, dtype, mel_host, f0_norm_host, bins_host);
+    if (rc != SSFE_OK) {
+        // a sub-batch failed after earlier ones were queued: their uploads read and their downloads write the
+        // caller's host buffers, so nothing may be in flight when the error reaches the caller
+        cudaStreamSynchronize(ctx->copy_in);
+        for (ssfe_ctx *ln : ctx->lane)
+            if (ln) cudaStreamSynchronize(ln->stream);
+        cudaStreamSynchronize(ctx->copy_out);
+    }
+    return rc;
 }

@@ -68,6 +68,39 @@ def _ptr(a, typ):
 
 
 _DT = {torch.float32: L.F32, torch.float64: L.F64, torch.int16: L.I16}
+_NP_DT = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64, np.dtype(np.int16): L.I16}
+
+
+def _wav_dtype(table, dt):
+    if dt not in table:
+        raise TypeError("samples must be float32, float64 or int16 PCM, not %s" % (dt,))
+    return table[dt]
+
+
+def _check_ragged(off, numel, what="sample_offsets"):
+    """The C ABI takes plain pointers: offsets that leave the buffer would be an out-of-bounds device
+    read, so they are refused here (the reference indexes numpy arrays, which raise by themselves)."""
+    if off.ndim != 1 or off.shape[0] < 1:
+        raise ValueError("%s must be a 1-D array of n + 1 offsets" % what)
+    if off[0] < 0 or np.any(np.diff(off) < 0):
+        raise ValueError("%s must be non-negative and non-decreasing" % what)
+    if int(off[-1]) > int(numel):
+        raise ValueError("%s end at %d but the buffer holds %d elements" % (what, int(off[-1]), int(numel)))
+
+
+def _check_out(name, a, shape, dtype, device=None):
+    """A caller-supplied output buffer must be exactly what the kernels write: shape, dtype, dense."""
+    if isinstance(a, torch.Tensor):
+        ok = tuple(a.shape) == tuple(shape) and a.dtype == dtype and a.is_contiguous() and \
+            (device is None or a.device == device) and (device is not None or a.device.type == "cpu")
+    else:
+        npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int64: np.int64}[dtype]
+        ok = device is None and isinstance(a, np.ndarray) and a.shape == tuple(shape) and a.dtype == npdt and \
+            a.flags.c_contiguous and a.flags.writeable
+    if not ok:
+        raise ValueError("output buffer %r must be a dense %s array of shape %s%s" %
+                         (name, str(dtype).replace("torch.", ""), tuple(shape),
+                          "" if device is None else " on %s" % (device,)))
 
 
 class FrontEnd:
@@ -169,13 +202,14 @@ class FrontEnd:
         """make_spect_f0.py:52-54 on a ragged batch -> float64 tensor [fixed total]."""
         x = self._dev(x)
         so = _i64(sample_offsets)
+        _check_ragged(so, x.numel())
         n = so.shape[0] - 1
         fix, _ = self.plan(so)
         y = torch.empty(int(fix[-1]), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             self._bind_stream()
-            self._check(self.lib.ssfe_filtfilt(self._h, L.vp(x.data_ptr()), _DT[x.dtype], _ptr(so, L.c_i64p), n,
-                                               L.vp(y.data_ptr())))
+            self._check(self.lib.ssfe_filtfilt(self._h, L.vp(x.data_ptr()), _wav_dtype(_DT, x.dtype),
+                                               _ptr(so, L.c_i64p), n, L.vp(y.data_ptr())))
         return y, fix
 
     def rand(self, seeds, skips, counts):
@@ -194,6 +228,7 @@ class FrontEnd:
     def _stft(self, fn, width, wav, offsets):
         wav = self._dev(wav, torch.float32)
         off = _i64(offsets)
+        _check_ragged(off, wav.numel(), "offsets")
         n = off.shape[0] - 1
         frames = (np.diff(off) + self.config.hop) // self.config.hop
         out = torch.empty((int(frames.sum()), width), dtype=torch.float32, device=self.device)
@@ -214,6 +249,7 @@ class FrontEnd:
         """make_spect_f0.py:64: log-F0 float32 [sum ceil(L/256)], unvoiced -1e10.  wav is NOT pre-scaled."""
         wav = self._dev(wav, torch.float32)
         off = _i64(offsets)
+        _check_ragged(off, wav.numel(), "offsets")
         n = off.shape[0] - 1
         lo = np.ascontiguousarray(f0_lo, dtype=np.float32)
         hi = np.ascontiguousarray(f0_hi, dtype=np.float32)
@@ -307,6 +343,7 @@ class FrontEnd:
         """
         x = self._dev(x)
         b, keep = self._batch(sample_offsets, f0_lo, f0_hi, spk_seed, dither_skip)
+        _check_ragged(keep["so"], x.numel())
         fix, fr = self.plan(keep["so"])
         T, S = int(fr[-1]), int(fix[-1])
         shapes = dict(mel=((T, self.config.n_mels), torch.float32), f0_norm=((T,), torch.float32),
@@ -317,13 +354,17 @@ class FrontEnd:
         o = L.Outputs()
         for k in want:
             shp, dt = shapes[k]
-            t = out[k] if out is not None and k in out else torch.empty(shp, dtype=dt, device=self.device)
+            if out is not None and k in out:
+                t = out[k]
+                _check_out(k, t, shp, dt, self.device)
+            else:
+                t = torch.empty(shp, dtype=dt, device=self.device)
             res[k] = t
             setattr(o, k, t.data_ptr())
         with torch.cuda.device(self.device):
             self._bind_stream()
-            self._check(self.lib.ssfe_extract(self._h, ctypes.byref(b), L.vp(x.data_ptr()), _DT[x.dtype],
-                                              ctypes.byref(o)))
+            self._check(self.lib.ssfe_extract(self._h, ctypes.byref(b), L.vp(x.data_ptr()),
+                                              _wav_dtype(_DT, x.dtype), ctypes.byref(o)))
         res["fixed_offsets"], res["frame_offsets"] = fix, fr
         return res
 
@@ -331,19 +372,25 @@ class FrontEnd:
         """Same with HOST buffers (numpy arrays or pinned torch CPU tensors) in and out."""
         if isinstance(x_host, torch.Tensor):
             xt = x_host
-            assert xt.device.type == "cpu" and xt.is_contiguous()
-            ptr, dt = xt.data_ptr(), _DT[xt.dtype]
+            if xt.device.type != "cpu" or not xt.is_contiguous():
+                raise ValueError("extract_host takes a dense CPU tensor (use extract for device tensors)")
+            ptr, dt, numel = xt.data_ptr(), _wav_dtype(_DT, xt.dtype), xt.numel()
         else:
             x_host = np.ascontiguousarray(x_host)
-            ptr = x_host.ctypes.data
-            dt = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64, np.dtype(np.int16): L.I16}[x_host.dtype]
+            ptr, dt, numel = x_host.ctypes.data, _wav_dtype(_NP_DT, x_host.dtype), x_host.size
         b, keep = self._batch(sample_offsets, f0_lo, f0_hi, spk_seed, dither_skip)
+        _check_ragged(keep["so"], numel)
         fix, fr = self.plan(keep["so"])
         T = int(fr[-1])
         if out is None:
             out = dict(mel=np.empty((T, self.config.n_mels), np.float32), f0_norm=np.empty(T, np.float32))
             if want_bins:
                 out["bins"] = np.empty(T, np.int64)
+        else:
+            _check_out("mel", out["mel"], (T, self.config.n_mels), torch.float32)
+            _check_out("f0_norm", out["f0_norm"], (T,), torch.float32)
+            if out.get("bins") is not None:
+                _check_out("bins", out["bins"], (T,), torch.int64)
 
         def hp(a):
             if a is None:

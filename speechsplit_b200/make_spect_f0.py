@@ -22,30 +22,36 @@ from .sharding import fixed_length
 
 
 def read_wav(path):
-    """-> (int16 or float array, fs).  16-bit PCM stays int16 (x = v/32768 exactly, like sf.read)."""
+    """-> (int16 or float64 array, fs).  16-bit PCM stays int16 (x = v/32768 exactly, like sf.read);
+    any other sample format goes through soundfile as float64, as at make_spect_f0.py:50."""
     try:
         import soundfile as sf
-        x, fs = sf.read(path, dtype="int16")
-        return x, fs
     except ImportError:
-        with wave.open(path, "rb") as w:
-            fs, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-            raw = w.readframes(n)
-        if sw != 2 or nch != 1:
-            raise ValueError("%s: only 16-bit mono PCM is supported without soundfile" % path)
-        return np.frombuffer(raw, dtype="<i2"), fs
+        sf = None
+    if sf is not None:
+        if sf.info(path).subtype == "PCM_16":
+            return sf.read(path, dtype="int16")
+        return sf.read(path)
+    with wave.open(path, "rb") as w:
+        fs, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+        raw = w.readframes(n)
+    if sw != 2 or nch != 1:
+        raise ValueError("%s: only 16-bit mono PCM is supported without soundfile" % path)
+    return np.frombuffer(raw, dtype="<i2"), fs
 
 
 def extract_speakers(fe, speakers, max_utts_per_call=4096):
-    """speakers: list of (spk_name, gender, [arrays in sorted file order]).  Yields
+    """speakers: iterable of (spk_name, gender, [arrays in sorted file order]), consumed lazily.  Yields
     (spk_name, file_index, S (T,80) f32, f0_norm (T,) f32) in the reference's loop order."""
     batch, meta = [], []
 
     def flush():
         if not batch:
             return
-        dt = np.int16 if all(a.dtype == np.int16 for a in batch) else np.float64
-        x = np.concatenate([a.astype(dt) if dt == np.int16 else (a.astype(np.float64) / 32768.0 if a.dtype == np.int16 else a.astype(np.float64)) for a in batch])
+        if all(a.dtype == np.int16 for a in batch):
+            x = np.concatenate(batch)
+        else:       # mixed sample formats: everything as the float64 sf.read would have returned
+            x = np.concatenate([a / 32768.0 if a.dtype == np.int16 else a.astype(np.float64) for a in batch])
         off = np.concatenate([[0], np.cumsum([len(a) for a in batch])]).astype(np.int64)
         lo = [GENDER_RANGE[m[1]][0] for m in meta]
         hi = [GENDER_RANGE[m[1]][1] for m in meta]
@@ -77,22 +83,26 @@ def make_spect_f0(root_dir="assets/wavs", target_dir="assets/spmel", target_dir_
     dir_name, subdirs, _ = next(os.walk(root_dir))             # :28
     if verbose:
         print("Found directory: %s" % dir_name)
-    speakers, names = [], {}
-    for subdir in sorted(subdirs):                             # :31
-        if verbose:
-            print(subdir)
-        os.makedirs(os.path.join(target_dir, subdir), exist_ok=True)
-        os.makedirs(os.path.join(target_dir_f0, subdir), exist_ok=True)
-        _, _, files = next(os.walk(os.path.join(dir_name, subdir)))
-        files = sorted(files)                                  # :48
-        utts = []
-        for f in files:
-            x, fs = read_wav(os.path.join(dir_name, subdir, f))
-            assert fs == 16000                                 # :51
-            utts.append(x)
-        speakers.append((subdir, spk2gen[subdir], utts))
-        names[subdir] = files
-    for spk, k, S, f0n in extract_speakers(fe, speakers):
+    names = {}
+
+    def speakers():
+        # read lazily: extract_speakers holds at most one call's worth of utterances plus one speaker
+        for subdir in sorted(subdirs):                         # :31
+            if verbose:
+                print(subdir)
+            os.makedirs(os.path.join(target_dir, subdir), exist_ok=True)
+            os.makedirs(os.path.join(target_dir_f0, subdir), exist_ok=True)
+            _, _, files = next(os.walk(os.path.join(dir_name, subdir)))
+            files = sorted(files)                              # :48
+            utts = []
+            for f in files:
+                x, fs = read_wav(os.path.join(dir_name, subdir, f))
+                assert fs == 16000                             # :51
+                utts.append(x)
+            names[subdir] = files
+            yield subdir, spk2gen[subdir], utts
+
+    for spk, k, S, f0n in extract_speakers(fe, speakers()):
         stem = names[spk][k][:-4]
         np.save(os.path.join(target_dir, spk, stem), S.astype(np.float32), allow_pickle=False)        # :71-72
         np.save(os.path.join(target_dir_f0, spk, stem), f0n.astype(np.float32), allow_pickle=False)   # :73-74

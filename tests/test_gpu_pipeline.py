@@ -187,6 +187,48 @@ def test_extract_errors(fe):
         fe.extract(torch.zeros(5000, dtype=torch.int16), [0, 5000], [70.0], [250.0], [226], [0])   # not M / F
 
 
+def test_extract_refuses_bad_buffers(fe):
+    """Offsets that leave the sample buffer and output buffers of the wrong shape never reach the C ABI."""
+    x = torch.zeros(5000, dtype=torch.int16)
+    with pytest.raises(ValueError):
+        fe.extract(x, [0, 5001], [50.0], [250.0], [226], [0])
+    with pytest.raises(ValueError):
+        fe.extract_host(x.numpy(), [0, 5001], [50.0], [250.0], [226], [0])
+    with pytest.raises(TypeError):
+        fe.extract(torch.zeros(5000, dtype=torch.int32), [0, 5000], [50.0], [250.0], [226], [0])
+    with pytest.raises(ValueError):
+        fe.extract(x, [0, 5000], [50.0], [250.0], [226], [0],
+                   out=dict(mel=torch.empty((19, 80), device="cuda")))       # 5000 samples are 20 frames
+    with pytest.raises(ValueError):
+        fe.extract_host(x.numpy(), [0, 5000], [50.0], [250.0], [226], [0],
+                        out=dict(mel=np.empty((20, 80), np.float64), f0_norm=np.empty(20, np.float32)))
+
+
+def test_extract_host_error_in_later_sub_batch(golden_dir, monkeypatch):
+    """A sub-batch that fails after earlier ones were queued: the error surfaces as the reference's
+    ValueError, nothing is left in flight on the caller's buffers, and the context stays usable."""
+    from speechsplit_b200 import FrontEnd
+    monkeypatch.setenv("SSFE_HOST_CHUNK_SAMPLES", "1000")
+    f2 = FrontEnd(0)
+    try:
+        pcm, meta = _golden_batch(golden_dir, NAMES)
+        lo = [50.0 if m["gender"] == "M" else 100.0 for m in meta]
+        hi = [250.0 if m["gender"] == "M" else 600.0 for m in meta]
+        seed, skip = [int(m["spk"][1:]) for m in meta], [m["skip"] for m in meta]
+        off = np.concatenate([[0], np.cumsum([len(p) for p in pcm])]).astype(np.int64)
+        good = f2.extract_host(np.concatenate(pcm), off, lo, hi, seed, skip)
+        # same batch with a 500-sample utterance of another speaker appended: too short for get_f0
+        bad_pcm = pcm + [np.zeros(500, np.int16)]
+        bad_off = np.concatenate([off, [off[-1] + 500]]).astype(np.int64)
+        with pytest.raises(ValueError):
+            f2.extract_host(np.concatenate(bad_pcm), bad_off, lo + [50.0], hi + [250.0], seed + [999], skip + [0])
+        again = f2.extract_host(np.concatenate(pcm), off, lo, hi, seed, skip)
+        for k in ("mel", "f0_norm", "bins"):
+            assert np.array_equal(again[k], good[k], equal_nan=True), k
+    finally:
+        f2.close()
+
+
 def test_make_spect_f0_script_drop_in(tmp_path):
     """The script form (speechsplit_b200.make_spect_f0) against the reference's loop run on the oracle:
     a tree of 16-bit mono WAVs + spk2gen.pkl in, spmel/ and raptf0/ trees of NPY v1.0 '<f4' out
