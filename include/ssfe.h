@@ -196,7 +196,9 @@ int ssfe_extract(ssfe_ctx *ctx, const ssfe_batch *batch, const void *x_dev, int 
 
 /* Same, HOST buffers in and out: x_host (pageable or pinned), outputs are host pointers
  * (onehot/wav/wav64 not offered here; bins optional).  The call stages through pinned memory,
- * overlaps H2D / kernels / D2H over sub-batches and returns when the results are in host memory. */
+ * overlaps H2D / kernels / D2H over sub-batches and returns when the results are in host memory.
+ * On error nothing is left in flight on the caller's buffers either: the call drains its streams
+ * before it returns the code (sub-batches queued before the failing one may have been written). */
 int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *batch, const void *x_host, int dtype,
                       float *mel_host, float *f0_norm_host, int64_t *bins_host);
 
