@@ -413,6 +413,13 @@ class FrontEnd:
         left = np.ascontiguousarray(left, dtype=np.int32)
         len_crop = np.ascontiguousarray(len_crop, dtype=np.int32)
         n = utt.shape[0]
+        if left.shape[0] != n or len_crop.shape[0] != n:
+            raise ValueError("collate: utt, left and len_crop must have one entry per item")
+        _check_ragged(fo, f0_norm.numel(), "frame_offsets")
+        if mel.numel() != f0_norm.numel() * self.config.n_mels:
+            raise ValueError("collate: mel must hold %d values per F0 frame" % self.config.n_mels)
+        if n and (utt.min() < 0 or utt.max() >= fo.shape[0] - 1):
+            raise ValueError("collate: utterance index out of range (%d utterances)" % (fo.shape[0] - 1))
         melsp = torch.empty((n, max_len_pad, self.config.n_mels), dtype=torch.float32, device=self.device)
         pitch = torch.empty((n, max_len_pad, 1), dtype=torch.float32, device=self.device)
         onehot = torch.empty((n, max_len_pad, 257), dtype=torch.float32, device=self.device) if want_onehot else None

@@ -302,3 +302,43 @@ def test_collate_matches_data_loader(fe):
         assert np.array_equal(bins[i].cpu().numpy(), idx) and np.array_equal(onehot[i].cpu().numpy(), enc)
     with pytest.raises(Exception):
         fe.collate(mel, f0, foff, [0], [100], [128], 192)        # crop runs past the utterance
+
+
+def test_loader_mirror_on_gpu(fe, tmp_path):
+    """speechsplit_b200.data_loader (get_loader -> Utterances / MyCollator, features resident in HBM, one
+    ssfe_collate launch per batch) against the reference's collator loop (data_loader.py:101-128) on the
+    same numpy seed: identical melsp / spk_emb / pitch / len_org, as CUDA tensors of the shapes and dtypes
+    solver.py:142 unpacks; the optional one-hot equals quantize_f0_torch of the padded pitch (solver.py:162)."""
+    from types import SimpleNamespace
+
+    from speechsplit_b200.data_loader import get_loader, make_metadata
+    from test_host_checks import _feature_tree, _reference_collate
+
+    _feature_tree(tmp_path, {"p225": [150, 400], "p226": [200], "p227": [135, 140], "p228": [129]})
+    make_metadata(str(tmp_path / "spmel"), verbose=False)
+    hp = SimpleNamespace(root_dir=str(tmp_path / "spmel"), feat_dir=str(tmp_path / "raptf0"), mode="train",
+                         batch_size=16, shuffle=True, num_workers=0, samplier=8, min_len_seq=64, max_len_seq=128,
+                         max_len_pad=192)
+    loader = get_loader(hp, frontend=fe, want_onehot=True)
+    ds = loader.dataset
+    assert len(loader) == (4 * 8) // 16
+    torch.manual_seed(5)
+    np.random.seed(21)
+    n_launch = fe.launch_count
+    got, onehots = [], []
+    for batch in loader:
+        got.append(batch)
+        onehots.append(loader.collate_fn.last_onehot)
+    assert fe.launch_count - n_launch <= 5 * len(got)          # the collate kernel + its metadata copies
+    order = list(loader.sampler.sample_idx_array.numpy())       # the shuffled pass the loader just made
+    assert sorted(order) == sorted(list(range(4)) * 8) and order != sorted(order)
+    np.random.seed(21)
+    for b, (batch, (onehot, bins)) in enumerate(zip(got, onehots)):
+        want = _reference_collate([tuple(ds[i]) for i in order[16 * b: 16 * b + 16]], 64, 128, 192)
+        for g, w, shape, dt in zip(batch, want, [(16, 192, 80), (16, 82), (16, 192, 1), (16,)],
+                                   [torch.float32, torch.float32, torch.float32, torch.int64]):
+            assert g.is_cuda and tuple(g.shape) == shape and g.dtype == dt
+            assert torch.equal(g.cpu(), w)
+        enc, idx = rp.quantize_f0_numpy(want[2].numpy().reshape(-1))
+        assert np.array_equal(onehot.cpu().numpy().reshape(-1, 257), enc)
+        assert np.array_equal(bins.cpu().numpy().reshape(-1), idx)

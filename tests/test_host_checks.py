@@ -3,6 +3,8 @@
 The C ABI takes plain pointers and sizes (include/ssfe.h), so everything the reference gets for free
 from numpy indexing - offsets that leave the buffer, output buffers of the wrong shape or dtype - has to
 be refused before a pointer crosses the boundary."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -155,3 +157,129 @@ def test_script_form_batches_are_bounded():
     assert [c["n"] for c in fake.calls] == [2, 2, 2]
     assert [c["skip"] for c in fake.calls] == [[0, 1000], [2000, 0], [1000, 2000]]
     assert [c["seed"] for c in fake.calls] == [[226, 226], [226, 227], [227, 227]]
+
+
+# ---- data_loader / make_metadata mirror (host logic; the crop / clip / pad arithmetic is -m gpu) ----------
+class _NumpyCollateFrontEnd:
+    """Test double for FrontEnd in the loader tests: `_dev` keeps arrays on the host and `collate` is the
+    reference's own per-item numpy code (data_loader.py:108-116), so that the HOST side of the mirror - the
+    draws, the indices handed to the kernel, the batch layout - can be compared with the reference loop."""
+
+    def _dev(self, a, dtype=None):
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    def collate(self, mel, f0, off, utt, left, len_crop, max_len_pad, want_onehot=False):
+        mel, f0 = mel.numpy(), f0.numpy()
+        a_all, c_all = [], []
+        for u, l, n in zip(utt, left, len_crop):
+            a = np.clip(mel[off[u] + l: off[u] + l + n], 0, 1)
+            c = f0[off[u] + l: off[u] + l + n]
+            a_all.append(np.pad(a, ((0, max_len_pad - n), (0, 0)), "constant"))
+            c_all.append(np.pad(c[:, None], ((0, max_len_pad - n), (0, 0)), "constant", constant_values=-1e10))
+        return torch.from_numpy(np.stack(a_all)), torch.from_numpy(np.stack(c_all)), None, None
+
+
+def _feature_tree(tmp_path, spec, seed=3):
+    rng = np.random.default_rng(seed)
+    feats = {}
+    for spk, Ts in spec.items():
+        (tmp_path / "spmel" / spk).mkdir(parents=True)
+        (tmp_path / "raptf0" / spk).mkdir(parents=True)
+        for k, T in enumerate(Ts):
+            S = (rng.random((T, 80)) * 1.3 - 0.15).astype(np.float32)
+            f0 = rng.random(T).astype(np.float32)
+            f0[rng.random(T) < 0.3] = -1e10
+            name = "%s_%03d.npy" % (spk, 9 - k)
+            np.save(tmp_path / "spmel" / spk / name, S, allow_pickle=False)
+            np.save(tmp_path / "raptf0" / spk / name, f0, allow_pickle=False)
+            feats[(spk, name)] = (S, f0)
+    return feats
+
+
+def _reference_collate(batch, min_len_seq, max_len_seq, max_len_pad):
+    """data_loader.py:101-128 as written (minus the stray pdb line), on host arrays."""
+    new_batch = []
+    for aa, b, c in batch:
+        len_crop = np.random.randint(min_len_seq, max_len_seq + 1, size=2)
+        left = np.random.randint(0, len(aa) - len_crop[0], size=2)
+        a = np.clip(aa[left[0]:left[0] + len_crop[0], :], 0, 1)
+        c = c[left[0]:left[0] + len_crop[0]]
+        a_pad = np.pad(a, ((0, max_len_pad - a.shape[0]), (0, 0)), "constant")
+        c_pad = np.pad(c[:, np.newaxis], ((0, max_len_pad - c.shape[0]), (0, 0)), "constant", constant_values=-1e10)
+        new_batch.append((a_pad, b, c_pad, len_crop[0]))
+    a, b, c, d = zip(*new_batch)
+    return (torch.from_numpy(np.stack(a, axis=0)), torch.from_numpy(np.stack(b, axis=0)),
+            torch.from_numpy(np.stack(c, axis=0)), torch.from_numpy(np.stack(d, axis=0)))
+
+
+def test_make_metadata_layout(tmp_path):
+    """make_metadata.py:10-33: sorted speakers, [name, one-hot(82) f32, sorted 'spk/file.npy'...], train.pkl."""
+    import pickle
+
+    from speechsplit_b200.data_loader import make_metadata
+    _feature_tree(tmp_path, {"p300": [150, 140], "p226": [200]})
+    meta = make_metadata(str(tmp_path / "spmel"), verbose=False)
+    with open(tmp_path / "spmel" / "train.pkl", "rb") as f:
+        disk = pickle.load(f)
+    assert [m[0] for m in meta] == ["p226", "p300"] == [m[0] for m in disk]
+    assert meta[0][2:] == [os.path.join("p226", "p226_009.npy")]
+    assert meta[1][2:] == [os.path.join("p300", "p300_008.npy"), os.path.join("p300", "p300_009.npy")]
+    for m, hot in zip(meta, (1, 7)):
+        assert m[1].dtype == np.float32 and m[1].shape == (82,) and m[1].sum() == 1.0 and m[1][hot] == 1.0
+    assert np.array_equal(disk[1][1], meta[1][1])
+
+
+def test_loader_mirror_host_logic(tmp_path):
+    """Utterances / MyCollator / MultiSampler / get_loader against the reference's loop on the same seed:
+    same items, same numpy draws in the same order, same batch layout and dtypes (solver.py:142)."""
+    from types import SimpleNamespace
+
+    from speechsplit_b200.data_loader import MultiSampler, Utterances, get_loader, make_metadata
+    feats = _feature_tree(tmp_path, {"p225": [150, 400], "p226": [200], "p227": [135, 140]})
+    make_metadata(str(tmp_path / "spmel"), verbose=False)
+    hp = SimpleNamespace(root_dir=str(tmp_path / "spmel"), feat_dir=str(tmp_path / "raptf0"), mode="train",
+                         batch_size=4, shuffle=False, num_workers=0, samplier=3, min_len_seq=64, max_len_seq=128,
+                         max_len_pad=192)
+    loader = get_loader(hp, frontend=_NumpyCollateFrontEnd())
+    ds = loader.dataset
+    # an item is a speaker with the FIRST file of its sorted list (data_loader.py:62-63)
+    assert len(ds) == 3 and len(loader) == (3 * 3) // 4
+    first = {"p225": "p225_008.npy", "p226": "p226_009.npy", "p227": "p227_008.npy"}
+    for i, spk in enumerate(sorted(first)):
+        melsp, emb, f0 = ds[i]
+        assert np.array_equal(melsp, feats[(spk, first[spk])][0]) and np.array_equal(f0, feats[(spk, first[spk])][1])
+        assert emb[1 if spk == "p226" else 7] == 1.0
+    order = list(MultiSampler(3, 3).gen_sample_array().numpy())
+    assert order == [0, 1, 2] * 3
+
+    np.random.seed(11)
+    ours = list(loader)
+    np.random.seed(11)
+    for b, got in enumerate(ours):
+        items = [tuple(ds[i]) for i in order[4 * b: 4 * b + 4]]
+        want = _reference_collate(items, 64, 128, 192)
+        assert len(got) == 4
+        for g, w, shape, dt in zip(got, want, [(4, 192, 80), (4, 82), (4, 192, 1), (4,)],
+                                   [torch.float32, torch.float32, torch.float32, torch.int64]):
+            assert tuple(g.shape) == shape and g.dtype == dt and w.dtype == dt
+            assert torch.equal(g, w)
+    assert len(ours) == 2
+
+    with pytest.raises(ValueError):
+        Utterances(hp.root_dir, hp.feat_dir, "valid")                    # data_loader.py:48-49
+    # 'test' mode keeps frames [:split] with split = 0, i.e. nothing (data_loader.py:67-69)
+    assert Utterances(hp.root_dir, hp.feat_dir, "test", frontend=_NumpyCollateFrontEnd())[0][0].shape == (0, 80)
+
+
+def test_collator_refuses_short_utterance(tmp_path):
+    """An utterance no longer than the drawn crop makes numpy's randint(0, <= 0) raise, as in the reference."""
+    from types import SimpleNamespace
+
+    from speechsplit_b200.data_loader import get_loader, make_metadata
+    _feature_tree(tmp_path, {"p225": [60]})
+    make_metadata(str(tmp_path / "spmel"), verbose=False)
+    hp = SimpleNamespace(root_dir=str(tmp_path / "spmel"), feat_dir=str(tmp_path / "raptf0"), mode="train",
+                         batch_size=1, shuffle=False, num_workers=0, samplier=1, min_len_seq=64, max_len_seq=128,
+                         max_len_pad=192)
+    with pytest.raises(ValueError):
+        next(iter(get_loader(hp, frontend=_NumpyCollateFrontEnd())))
