@@ -395,6 +395,61 @@ def run_ours(args):
                    "batch": 16, "max_len_pad": 192,
                    "step": "crop + clip + pad + one-hot (data_loader.py:101-128, solver.py:162) + InterpLnr (model.py:380-436)"}
 
+        # the same step through the reference-facing loader API (speechsplit_b200.data_loader.get_loader over
+        # spmel / raptf0 NPY trees + train.pkl): one item per speaker = its first file, as data_loader.py:62-63
+        import shutil
+        from types import SimpleNamespace
+        from speechsplit_b200.data_loader import get_loader, make_metadata
+        tmp = tempfile.mkdtemp(prefix="ssfe_loader_")
+        try:
+            seen = set()
+            for i, m in enumerate(mine):
+                if m.spk in seen or frs[i] <= 130:
+                    continue
+                seen.add(m.spk)
+                for sub, t in (("spmel", outs["mel"]), ("raptf0", outs["f0_norm"])):
+                    os.makedirs(os.path.join(tmp, sub, m.spk), exist_ok=True)
+                    np.save(os.path.join(tmp, sub, m.spk, "%s_001.npy" % m.spk), t[fr[i]:fr[i + 1]].cpu().numpy(),
+                            allow_pickle=False)
+            make_metadata(os.path.join(tmp, "spmel"), verbose=False)
+            n_batches = 220
+            hp = SimpleNamespace(root_dir=os.path.join(tmp, "spmel"), feat_dir=os.path.join(tmp, "raptf0"), mode="train",
+                                 batch_size=16, shuffle=True, num_workers=0, samplier=-(-16 * n_batches // len(seen)),
+                                 min_len_seq=64, max_len_seq=128, max_len_pad=192)
+            loader = get_loader(hp, frontend=fe, want_onehot=True)
+            it = iter(loader)
+
+            def loader_step():
+                melsp, emb, pitch, len_org = next(it)                       # solver.py:142
+                return interp(torch.cat((melsp, pitch), dim=-1), len_org)   # solver.py:160-161
+
+            for _ in range(20):
+                loader_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c0.record()
+            for _ in range(n_batches - 20):
+                loader_step()
+            c1.record()
+            torch.cuda.synchronize()
+            collate["loader_steps_per_s_device"] = (n_batches - 20) / (c0.elapsed_time(c1) * 1e-3)
+            collate["loader_steps_per_s_wall"] = (n_batches - 20) / (time.perf_counter() - t0)
+            collate["loader"] = "speechsplit_b200.data_loader.get_loader, %d speakers, features resident in HBM" % len(seen)
+            if not args.no_cpu_baseline:
+                # the reference's collator loop + quantisation on one host core (its loader default is num_workers=0)
+                from oracle import collate_ref, ref_pipeline
+                items = [tuple(loader.dataset[i]) for i in range(len(loader.dataset))]
+                t0, nb = time.perf_counter(), 0
+                while time.perf_counter() - t0 < 3.0:
+                    bt = [items[j] for j in rng.integers(0, len(items), 16)]
+                    _, _, pitch_ref, _ = collate_ref.collate(bt, 64, 128, 192)
+                    ref_pipeline.quantize_f0_numpy(pitch_ref.reshape(-1))
+                    nb += 1
+                collate["cpu_steps_per_s"] = nb / (time.perf_counter() - t0)
+                collate["cpu_step"] = "oracle.collate_ref (data_loader.py:101-128) + quantize_f0_numpy, 1 core, no InterpLnr"
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -11,6 +11,8 @@ What is reference-produced (pins the oracle and the CUDA path):
                      reference's butter_highpass + pySTFT + scipy filtfilt + numpy RandomState
   interp_lnr.npz     inputs, captured random draws and output of the reference's model.InterpLnr
                      (model.py:380-436) in training mode
+  collate.npz        inputs, numpy seed and output batch of the reference's data_loader.MyCollator
+                     (data_loader.py:96-128) and the train.pkl of the reference's make_metadata.py
 What is NOT reference-produced (librosa / pysptk are absent):
   the mel basis (oracle/mel_basis.py restatement) used inside pipeline_*.npz, and the
   ``f0_rapt`` arrays (oracle/rapt_ref.c restatement) - stored as regression vectors and
@@ -141,9 +143,66 @@ def interp_lnr():
     np.savez_compressed(os.path.join(HERE, "interp_lnr.npz"), **out)
 
 
+def collator():
+    """The reference's own data_loader.MyCollator and make_metadata.py, run unmodified.  Two things are
+    supplied from outside, neither touches their arithmetic: the name ``pdb`` (data_loader.py:106 calls
+    ``pdb.set_trace()`` but the module never imports pdb - a no-op object is put into the module's globals),
+    and a working directory that holds ``assets/spmel`` (make_metadata.py is a script with relative paths)."""
+    import pickle
+    import runpy
+    import tempfile
+
+    import data_loader as ref_dl  # the reference's own module
+    ref_dl.pdb = types.SimpleNamespace(set_trace=lambda: None)
+
+    class HP:
+        min_len_seq, max_len_seq, max_len_pad = 64, 128, 192
+
+    rng = np.random.Generator(np.random.PCG64(99))
+    Ts = [135, 200, 129, 400, 131]
+    out = {"n": len(Ts), "seed": 314, "order": np.array([3, 0, 4, 1, 2, 3, 3, 1], np.int64)}
+    items = []
+    for k, T in enumerate(Ts):
+        S = (rng.random((T, 80)) * 1.3 - 0.15).astype(np.float32)
+        f0 = rng.random(T).astype(np.float32)
+        f0[rng.random(T) < 0.3] = -1e10
+        emb = np.zeros(82, np.float32)
+        emb[1 if k == 1 else 7] = 1.0
+        out["S%d" % k], out["f0%d" % k], out["emb%d" % k] = S, f0, emb
+        items.append((S, emb, f0))
+    np.random.seed(int(out["seed"]))
+    melsp, spk_emb, pitch, len_org = ref_dl.MyCollator(HP)([items[i] for i in out["order"]])
+    out["melsp"], out["spk_emb"], out["pitch"], out["len_org"] = (melsp.numpy(), spk_emb.numpy(), pitch.numpy(),
+                                                                   len_org.numpy())
+    # make_metadata.py in a scratch tree: speakers and files created in non-sorted order
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        tree = {"p300": ["p300_010.npy", "p300_002.npy"], "p226": ["p226_005.npy"], "p225": ["p225_003.npy", "p225_001.npy", "p225_002.npy"]}
+        for spk, files in tree.items():
+            os.makedirs(os.path.join(tmp, "assets", "spmel", spk))
+            for f in files:
+                np.save(os.path.join(tmp, "assets", "spmel", spk, f), np.zeros((1, 80), np.float32))
+        os.chdir(tmp)
+        try:
+            runpy.run_path("/root/reference/make_metadata.py")
+        finally:
+            os.chdir(cwd)
+        with open(os.path.join(tmp, "assets", "spmel", "train.pkl"), "rb") as fh:
+            meta = pickle.load(fh)
+    out["meta_tree"] = np.array(["%s/%s" % (s, f) for s, fs in tree.items() for f in fs])
+    out["meta_speakers"] = np.array([m[0] for m in meta])
+    out["meta_emb"] = np.stack([m[1] for m in meta])
+    out["meta_files"] = np.array(["|".join(m[2:]) for m in meta])
+    np.savez_compressed(os.path.join(HERE, "collate.npz"), **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["collate"]:          # only the loader vectors (the others are unchanged)
+        collator()
+        sys.exit(0)
     utils_kat()
     interp_lnr()
+    collator()
     # cfg1: one 3.000 s male utterance, speaker p226 (+ two more files of the same speaker so the
     # dither stream continuity and the L % 256 == 0 append path are pinned)
     pipeline("pipeline_p226.npz", [UttMeta("p226", "M", 0, 48000, 226000),

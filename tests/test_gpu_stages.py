@@ -342,3 +342,22 @@ def test_loader_mirror_on_gpu(fe, tmp_path):
         enc, idx = rp.quantize_f0_numpy(want[2].numpy().reshape(-1))
         assert np.array_equal(onehot.cpu().numpy().reshape(-1, 257), enc)
         assert np.array_equal(bins.cpu().numpy().reshape(-1), idx)
+
+
+def test_collator_golden_on_gpu(fe, tmp_path, golden_dir):
+    """MyCollator on the GPU == the batch the reference's OWN data_loader.MyCollator produced for the same
+    items and numpy seed (tests/golden/collate.npz): bit-exact melsp / spk_emb / pitch / len_org."""
+    from types import SimpleNamespace
+
+    from speechsplit_b200.data_loader import MyCollator, Utterances, make_metadata
+    from test_host_checks import _golden_tree
+
+    g = _golden_tree(tmp_path, golden_dir)
+    make_metadata(str(tmp_path / "spmel"), verbose=False)
+    ds = Utterances(str(tmp_path / "spmel"), str(tmp_path / "raptf0"), "train", frontend=fe)
+    col = MyCollator(SimpleNamespace(min_len_seq=64, max_len_seq=128, max_len_pad=192), ds)
+    np.random.seed(int(g["seed"]))
+    batch = col([ds[int(i)] for i in g["order"]])
+    for got, name in zip(batch, ("melsp", "spk_emb", "pitch", "len_org")):
+        assert got.is_cuda and got.cpu().numpy().dtype == g[name].dtype
+        assert np.array_equal(got.cpu().numpy(), g[name]), name

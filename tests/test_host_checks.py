@@ -197,19 +197,22 @@ def _feature_tree(tmp_path, spec, seed=3):
 
 
 def _reference_collate(batch, min_len_seq, max_len_seq, max_len_pad):
-    """data_loader.py:101-128 as written (minus the stray pdb line), on host arrays."""
-    new_batch = []
-    for aa, b, c in batch:
-        len_crop = np.random.randint(min_len_seq, max_len_seq + 1, size=2)
-        left = np.random.randint(0, len(aa) - len_crop[0], size=2)
-        a = np.clip(aa[left[0]:left[0] + len_crop[0], :], 0, 1)
-        c = c[left[0]:left[0] + len_crop[0]]
-        a_pad = np.pad(a, ((0, max_len_pad - a.shape[0]), (0, 0)), "constant")
-        c_pad = np.pad(c[:, np.newaxis], ((0, max_len_pad - c.shape[0]), (0, 0)), "constant", constant_values=-1e10)
-        new_batch.append((a_pad, b, c_pad, len_crop[0]))
-    a, b, c, d = zip(*new_batch)
-    return (torch.from_numpy(np.stack(a, axis=0)), torch.from_numpy(np.stack(b, axis=0)),
-            torch.from_numpy(np.stack(c, axis=0)), torch.from_numpy(np.stack(d, axis=0)))
+    """data_loader.py:101-128 through the oracle restatement (pinned by tests/golden/collate.npz)."""
+    from oracle import collate_ref
+    return tuple(torch.from_numpy(a) for a in collate_ref.collate(batch, min_len_seq, max_len_seq, max_len_pad))
+
+
+def _golden_tree(tmp_path, golden_dir):
+    """The items of tests/golden/collate.npz as a spmel / raptf0 tree: item k is the only file of speaker
+    number k (p226 is the one with the embedding at index 1), so dataset index == golden item index."""
+    g = np.load(os.path.join(golden_dir, "collate.npz"))
+    names = ["p225", "p226", "p227", "p228", "p229"]
+    for k, spk in enumerate(names):
+        (tmp_path / "spmel" / spk).mkdir(parents=True)
+        (tmp_path / "raptf0" / spk).mkdir(parents=True)
+        np.save(tmp_path / "spmel" / spk / (spk + "_001.npy"), g["S%d" % k], allow_pickle=False)
+        np.save(tmp_path / "raptf0" / spk / (spk + "_001.npy"), g["f0%d" % k], allow_pickle=False)
+    return g
 
 
 def test_make_metadata_layout(tmp_path):
@@ -283,3 +286,37 @@ def test_collator_refuses_short_utterance(tmp_path):
                          max_len_pad=192)
     with pytest.raises(ValueError):
         next(iter(get_loader(hp, frontend=_NumpyCollateFrontEnd())))
+
+
+def test_make_metadata_matches_reference(tmp_path, golden_dir):
+    """make_metadata against the train.pkl the reference's own make_metadata.py wrote for the same tree."""
+    from speechsplit_b200.data_loader import make_metadata
+    g = np.load(os.path.join(golden_dir, "collate.npz"))
+    for e in g["meta_tree"]:
+        spk, f = str(e).split("/")
+        (tmp_path / "spmel" / spk).mkdir(parents=True, exist_ok=True)
+        np.save(tmp_path / "spmel" / spk / f, np.zeros((1, 80), np.float32))
+    meta = make_metadata(str(tmp_path / "spmel"), verbose=False)
+    assert [m[0] for m in meta] == [str(x) for x in g["meta_speakers"]]
+    assert np.array_equal(np.stack([m[1] for m in meta]), g["meta_emb"]) and meta[0][1].dtype == np.float32
+    assert ["|".join(m[2:]) for m in meta] == [str(x) for x in g["meta_files"]]
+
+
+def test_collator_draws_match_reference(tmp_path, golden_dir):
+    """The crops MyCollator hands to the kernel are the ones the reference's own collator took: same
+    lengths (len_org of the golden batch) and same positions (the golden rows are found at `left`)."""
+    from types import SimpleNamespace
+
+    from speechsplit_b200.data_loader import MyCollator, Utterances, make_metadata
+    g = _golden_tree(tmp_path, golden_dir)
+    make_metadata(str(tmp_path / "spmel"), verbose=False)
+    ds = Utterances(str(tmp_path / "spmel"), str(tmp_path / "raptf0"), "train", frontend=_NumpyCollateFrontEnd())
+    col = MyCollator(SimpleNamespace(min_len_seq=64, max_len_seq=128, max_len_pad=192), ds)
+    np.random.seed(int(g["seed"]))
+    utt, left, len_crop = col.draw([ds[int(i)] for i in g["order"]])
+    assert np.array_equal(utt, g["order"]) and np.array_equal(len_crop, g["len_org"])
+    for b, (u, l, n) in enumerate(zip(utt, left, len_crop)):
+        assert np.array_equal(g["pitch"][b, :n, 0], g["f0%d" % u][l:l + n])
+    np.random.seed(int(g["seed"]))
+    melsp, spk_emb, pitch, len_org = col([ds[int(i)] for i in g["order"]])
+    assert torch.equal(spk_emb, torch.from_numpy(g["spk_emb"])) and torch.equal(len_org, torch.from_numpy(g["len_org"]))

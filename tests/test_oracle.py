@@ -150,3 +150,24 @@ def test_interp_lnr_oracle_matches_reference_module(golden_dir):
     for k in range(int(z["n"])):
         y = interp_lnr(z["x%d" % k], z["len_seq%d" % k], z["scales%d" % k], z["len_seg%d" % k])
         assert y.dtype == np.float32 and np.array_equal(y, z["y%d" % k]), k
+
+
+def test_collator_matches_reference(golden_dir):
+    """oracle.collate_ref == the reference's own data_loader.MyCollator (data_loader.py:96-128) on the same
+    items and the same numpy seed, and == the train.pkl of the reference's make_metadata.py."""
+    from oracle import collate_ref
+    g = np.load(os.path.join(golden_dir, "collate.npz"))
+    items = [(g["S%d" % k], g["emb%d" % k], g["f0%d" % k]) for k in range(int(g["n"]))]
+    np.random.seed(int(g["seed"]))
+    melsp, spk_emb, pitch, len_org = collate_ref.collate([items[i] for i in g["order"]], 64, 128, 192)
+    for got, name in ((melsp, "melsp"), (spk_emb, "spk_emb"), (pitch, "pitch"), (len_org, "len_org")):
+        assert got.dtype == g[name].dtype and np.array_equal(got, g[name]), name
+    assert melsp.shape == (8, 192, 80) and pitch.shape == (8, 192, 1) and len_org.dtype == np.int64
+    tree = {}
+    for e in g["meta_tree"]:
+        spk, f = str(e).split("/")
+        tree.setdefault(spk, []).append(f)
+    meta = collate_ref.metadata(tree)
+    assert [m[0] for m in meta] == [str(x) for x in g["meta_speakers"]]
+    assert np.array_equal(np.stack([m[1] for m in meta]), g["meta_emb"])
+    assert ["|".join(m[2:]) for m in meta] == [str(x) for x in g["meta_files"]]
