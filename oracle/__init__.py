@@ -10,8 +10,12 @@ Parity status:
     ``utils.py`` imported in the build container (tests/golden/make_golden.py).
   * InterpLnr (oracle/interp_lnr.py): PINNED - bit-identical to the reference's own ``model.InterpLnr``
     run in the build container on captured random draws (tests/golden/interp_lnr.npz).
+  * training collator and manifest (oracle/collate_ref.py): PINNED - bit-identical to the batch of the
+    reference's own ``data_loader.MyCollator`` and the ``train.pkl`` of its ``make_metadata.py``
+    (tests/golden/collate.npz).
   * stage a4 (librosa.filters.mel) and stage a6 (pysptk.sptk.rapt -> SPTK/Snack get_f0):
     PARITY UNPINNED - neither package (nor its source) exists in the build container, so
     these are restatements of the published algorithms, anchored on the reference's call
-    sites (make_spect_f0.py:15, :64) and an independent torchaudio cross-check for the mel.
+    sites (make_spect_f0.py:15, :64) and two independent cross-checks for the mel (torchaudio,
+    transformers.audio_utils).
 """
