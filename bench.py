@@ -416,25 +416,29 @@ def run_ours(args):
             hp = SimpleNamespace(root_dir=os.path.join(tmp, "spmel"), feat_dir=os.path.join(tmp, "raptf0"), mode="train",
                                  batch_size=16, shuffle=True, num_workers=0, samplier=-(-16 * n_batches // len(seen)),
                                  min_len_seq=64, max_len_seq=128, max_len_pad=192)
-            loader = get_loader(hp, frontend=fe, want_onehot=True)
-            it = iter(loader)
+            for mode in ("reference", "batched"):
+                loader = get_loader(hp, frontend=fe, want_onehot=True, draws=mode)
+                it = iter(loader)
 
-            def loader_step():
-                melsp, emb, pitch, len_org = next(it)                       # solver.py:142
-                return interp(torch.cat((melsp, pitch), dim=-1), len_org)   # solver.py:160-161
+                def loader_step():
+                    melsp, emb, pitch, len_org = next(it)                       # solver.py:142
+                    return interp(torch.cat((melsp, pitch), dim=-1), len_org)   # solver.py:160-161
 
-            for _ in range(20):
-                loader_step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            c0.record()
-            for _ in range(n_batches - 20):
-                loader_step()
-            c1.record()
-            torch.cuda.synchronize()
-            collate["loader_steps_per_s_device"] = (n_batches - 20) / (c0.elapsed_time(c1) * 1e-3)
-            collate["loader_steps_per_s_wall"] = (n_batches - 20) / (time.perf_counter() - t0)
-            collate["loader"] = "speechsplit_b200.data_loader.get_loader, %d speakers, features resident in HBM" % len(seen)
+                for _ in range(20):
+                    loader_step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                c0.record()
+                for _ in range(n_batches - 20):
+                    loader_step()
+                c1.record()
+                torch.cuda.synchronize()
+                key = "loader" if mode == "reference" else "loader_batched_draws"
+                collate[key + "_steps_per_s_device"] = (n_batches - 20) / (c0.elapsed_time(c1) * 1e-3)
+                collate[key + "_steps_per_s_wall"] = (n_batches - 20) / (time.perf_counter() - t0)
+            collate["loader"] = ("speechsplit_b200.data_loader.get_loader, %d speakers, features resident in HBM; "
+                                 "draws in the reference's order (two np.random.randint calls per item) / batched "
+                                 "(two per batch)" % len(seen))
             if not args.no_cpu_baseline:
                 # the reference's collator loop + quantisation on one host core (its loader default is num_workers=0)
                 from oracle import collate_ref, ref_pipeline

@@ -123,16 +123,30 @@ class Utterances(data.Dataset):
 class MyCollator(object):
     """data_loader.py:96-128 with the per-item numpy work replaced by one ``ssfe_collate`` launch."""
 
-    def __init__(self, hparams, dataset=None, want_onehot=False):
+    def __init__(self, hparams, dataset=None, want_onehot=False, draws="reference"):
         self.min_len_seq = hparams.min_len_seq
         self.max_len_seq = hparams.max_len_seq
         self.max_len_pad = hparams.max_len_pad
         self.dataset = dataset
         self.want_onehot = want_onehot
+        if draws not in ("reference", "batched"):
+            raise ValueError("draws must be 'reference' or 'batched'")
+        # 'reference': numpy's global generator, two randint calls per item in the reference's order - seeded
+        # runs see the reference's batches, at ~8 us per call.  'batched': the same two distributions drawn
+        # with two calls per BATCH (a different stream, so not the reference's crops for a given seed).
+        self.draws = draws
         self.last_onehot = None          # (onehot (B,pad,257), bins (B,pad)) of the latest batch, if asked for
 
     def draw(self, batch):
         """The random crops of :104-105, item by item in batch order: (utt, left, len_crop) int arrays."""
+        if self.draws == "batched":
+            utt = np.asarray([token.index for token in batch], np.int32)
+            n_frames = np.asarray([len(token[0]) for token in batch], np.int64)
+            len_crop = np.random.randint(self.min_len_seq, self.max_len_seq + 1, size=len(batch)).astype(np.int64)
+            if len(batch) and np.any(n_frames - len_crop <= 0):
+                raise ValueError("high <= 0")                       # what numpy raises in the reference loop
+            left = np.random.randint(0, np.maximum(n_frames - len_crop, 1)) if len(batch) else np.zeros(0, np.int64)
+            return utt, np.asarray(left, np.int32), len_crop
         utt, left, len_crop = [], [], []
         for token in batch:
             aa = token[0]
@@ -152,9 +166,15 @@ class MyCollator(object):
         melsp, pitch, onehot, bins = fe.collate(mel, f0, off, utt, left, len_crop.astype(np.int32),
                                                 self.max_len_pad, want_onehot=self.want_onehot)
         self.last_onehot = (onehot, bins) if self.want_onehot else None
-        spk_emb = emb[torch.as_tensor(utt, dtype=torch.int64, device=emb.device)] if len(utt) else emb[:0]
-        len_org = torch.as_tensor(len_crop, dtype=torch.int64, device=melsp.device)
-        return melsp, spk_emb, pitch, len_org
+        if not len(utt):
+            return melsp, emb[:0], pitch, torch.zeros(0, dtype=torch.int64, device=melsp.device)
+        # item indices and crop lengths go up as ONE small transfer; from pinned memory and non-blocking, so that
+        # the host does not wait for the previous batch's kernels (a pageable copy synchronises the stream)
+        meta = torch.empty((2, len(utt)), dtype=torch.int64, pin_memory=emb.is_cuda)
+        meta[0] = torch.from_numpy(utt.astype(np.int64))
+        meta[1] = torch.from_numpy(len_crop)
+        meta = meta.to(emb.device, non_blocking=True)
+        return melsp, emb.index_select(0, meta[0]), pitch, meta[1]
 
 
 class MultiSampler(Sampler):
@@ -179,12 +199,12 @@ class MultiSampler(Sampler):
         return self.num_samples * self.n_repeats
 
 
-def get_loader(hparams, frontend=None, want_onehot=False):
+def get_loader(hparams, frontend=None, want_onehot=False, draws="reference"):
     """data_loader.py:157-175.  The features live in HBM and a batch is one kernel launch, so the loader
     runs in the main process (``hparams.num_workers`` is the reference's default 0 here whatever it says:
     worker processes could not share the CUDA context) and there is nothing to pin."""
     dataset = Utterances(hparams.root_dir, hparams.feat_dir, hparams.mode, frontend=frontend)
-    my_collator = MyCollator(hparams, dataset, want_onehot=want_onehot)
+    my_collator = MyCollator(hparams, dataset, want_onehot=want_onehot, draws=draws)
     sampler = MultiSampler(len(dataset), hparams.samplier, shuffle=hparams.shuffle)
     return data.DataLoader(dataset=dataset, batch_size=hparams.batch_size, sampler=sampler, num_workers=0,
                            drop_last=True, pin_memory=False, collate_fn=my_collator)

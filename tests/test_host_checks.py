@@ -320,3 +320,38 @@ def test_collator_draws_match_reference(tmp_path, golden_dir):
     np.random.seed(int(g["seed"]))
     melsp, spk_emb, pitch, len_org = col([ds[int(i)] for i in g["order"]])
     assert torch.equal(spk_emb, torch.from_numpy(g["spk_emb"])) and torch.equal(len_org, torch.from_numpy(g["len_org"]))
+
+
+def test_collator_batched_draws(tmp_path):
+    """draws='batched': same distributions as data_loader.py:104-105 (length uniform on [min, max], left
+    uniform on [0, T - length)), two numpy calls per batch; crops always inside the utterance."""
+    from types import SimpleNamespace
+
+    from speechsplit_b200.data_loader import MyCollator, Utterances, make_metadata
+    _feature_tree(tmp_path, {"p225": [129], "p226": [300]})
+    make_metadata(str(tmp_path / "spmel"), verbose=False)
+    ds = Utterances(str(tmp_path / "spmel"), str(tmp_path / "raptf0"), "train", frontend=_NumpyCollateFrontEnd())
+    hp = SimpleNamespace(min_len_seq=64, max_len_seq=128, max_len_pad=192)
+    col = MyCollator(hp, ds, draws="batched")
+    np.random.seed(2)
+    lens, lefts = [], []
+    for _ in range(400):
+        utt, left, len_crop = col.draw([ds[0], ds[1], ds[1], ds[0]])
+        assert list(utt) == [0, 1, 1, 0] and left.dtype == np.int32 and len_crop.dtype == np.int64
+        assert np.all(left >= 0) and np.all(left + len_crop < np.array([129, 300, 300, 129]))
+        lens.append(len_crop)
+        lefts.append(left)
+    lens, lefts = np.concatenate(lens), np.stack(lefts)
+    assert lens.min() == 64 and lens.max() == 128 and abs(lens.mean() - 96.0) < 2.0
+    assert lefts[:, 1].max() > 200 and lefts[:, 0].max() <= 64
+    melsp, spk_emb, pitch, len_org = col([ds[1], ds[0]])
+    assert tuple(melsp.shape) == (2, 192, 80) and tuple(pitch.shape) == (2, 192, 1) and len_org.dtype == torch.int64
+    with pytest.raises(ValueError):
+        MyCollator(hp, ds, draws="fast")
+    _feature_tree(tmp_path / "short", {"p225": [100]})
+    make_metadata(str(tmp_path / "short" / "spmel"), verbose=False)
+    short = Utterances(str(tmp_path / "short" / "spmel"), str(tmp_path / "short" / "raptf0"), "train",
+                       frontend=_NumpyCollateFrontEnd())
+    with pytest.raises(ValueError):
+        for _ in range(200):                                     # a crop of >= 100 frames is drawn soon enough
+            MyCollator(hp, short, draws="batched").draw([short[0]])
