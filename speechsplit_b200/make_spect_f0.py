@@ -32,12 +32,30 @@ def read_wav(path):
         if sf.info(path).subtype == "PCM_16":
             return sf.read(path, dtype="int16")
         return sf.read(path)
-    with wave.open(path, "rb") as w:
-        fs, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-        raw = w.readframes(n)
-    if sw != 2 or nch != 1:
-        raise ValueError("%s: only 16-bit mono PCM is supported without soundfile" % path)
-    return np.frombuffer(raw, dtype="<i2"), fs
+    try:
+        with wave.open(path, "rb") as w:
+            fs, nch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n) if (sw == 2 and nch == 1) else None
+    except wave.Error:                      # e.g. IEEE-float WAV (format tag 3), which the stdlib does not read
+        raw, nch = None, 1
+    if raw is not None:
+        return np.frombuffer(raw, dtype="<i2"), fs
+    if nch != 1:
+        raise ValueError("%s: %d channels; the pipeline takes mono files (make_spect_f0.py:50-52)" % (path, nch))
+    # other sample formats: scipy's reader, scaled to [-1, 1) the way soundfile's float64 read does
+    from scipy.io import wavfile
+    fs, data = wavfile.read(path)
+    if data.ndim != 1:
+        raise ValueError("%s: the pipeline takes mono files (make_spect_f0.py:50-52)" % path)
+    if data.dtype == np.int16:
+        return data, fs
+    if data.dtype == np.uint8:
+        return (data.astype(np.float64) - 128.0) / 128.0, fs
+    if data.dtype == np.int32:              # 32-bit PCM, and 24-bit PCM left-justified in 32 bits
+        return data.astype(np.float64) / 2147483648.0, fs
+    if data.dtype in (np.float32, np.float64):
+        return data.astype(np.float64), fs
+    raise ValueError("%s: unsupported WAV sample format %s" % (path, data.dtype))
 
 
 def extract_speakers(fe, speakers, max_utts_per_call=4096):

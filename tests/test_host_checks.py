@@ -355,3 +355,39 @@ def test_collator_batched_draws(tmp_path):
     with pytest.raises(ValueError):
         for _ in range(200):                                     # a crop of >= 100 frames is drawn soon enough
             MyCollator(hp, short, draws="batched").draw([short[0]])
+
+
+def test_read_wav_sample_formats(tmp_path):
+    """read_wav without soundfile: 16-bit PCM stays int16 (x = v / 32768 exactly, what sf.read returns);
+    8 / 24 / 32-bit PCM and IEEE-float files come back as the float64 soundfile would give; stereo is refused."""
+    import wave
+
+    from scipy.io import wavfile
+
+    from speechsplit_b200.make_spect_f0 import read_wav
+    rng = np.random.default_rng(4)
+    v16 = rng.integers(-32768, 32768, 1000).astype(np.int16)
+    wavfile.write(tmp_path / "a16.wav", 16000, v16)
+    x, fs = read_wav(str(tmp_path / "a16.wav"))
+    assert fs == 16000 and x.dtype == np.int16 and np.array_equal(x, v16)
+    v32 = rng.integers(-2**31, 2**31, 1000).astype(np.int32)
+    wavfile.write(tmp_path / "a32.wav", 16000, v32)
+    x, _ = read_wav(str(tmp_path / "a32.wav"))
+    assert x.dtype == np.float64 and np.array_equal(x, v32 / 2147483648.0)
+    v8 = rng.integers(0, 256, 1000).astype(np.uint8)
+    wavfile.write(tmp_path / "a8.wav", 16000, v8)
+    x, _ = read_wav(str(tmp_path / "a8.wav"))
+    assert x.dtype == np.float64 and np.array_equal(x, (v8.astype(np.float64) - 128) / 128)
+    vf = (rng.random(1000) - 0.5).astype(np.float32)
+    wavfile.write(tmp_path / "af.wav", 16000, vf)
+    x, _ = read_wav(str(tmp_path / "af.wav"))
+    assert x.dtype == np.float64 and np.array_equal(x, vf.astype(np.float64))
+    v24 = rng.integers(-2**23, 2**23, 1000)
+    with wave.open(str(tmp_path / "a24.wav"), "wb") as w:
+        w.setnchannels(1), w.setsampwidth(3), w.setframerate(16000)
+        w.writeframes(b"".join(int(t).to_bytes(3, "little", signed=True) for t in v24))
+    x, _ = read_wav(str(tmp_path / "a24.wav"))
+    assert x.dtype == np.float64 and np.array_equal(x, v24 / 8388608.0)
+    wavfile.write(tmp_path / "st.wav", 16000, np.stack([v16, v16], 1))
+    with pytest.raises(ValueError):
+        read_wav(str(tmp_path / "st.wav"))
