@@ -13,6 +13,9 @@ What is reference-produced (pins the oracle and the CUDA path):
                      (model.py:380-436) in training mode
   collate.npz        inputs, numpy seed and output batch of the reference's data_loader.MyCollator
                      (data_loader.py:96-128) and the train.pkl of the reference's make_metadata.py
+  demo_kat.npz       the two real (VCTK p226 / p231) normalised-F0 tracks shipped in the reference's
+                     assets/demo.pkl - outputs of the ORIGINAL pipeline with the real pysptk / librosa - and
+                     what the reference's utils.pad_seq_to_2 + quantize_f0_numpy make of them (demo.ipynb:36-50)
 What is NOT reference-produced (librosa / pysptk are absent):
   the mel basis (oracle/mel_basis.py restatement) used inside pipeline_*.npz, and the
   ``f0_rapt`` arrays (oracle/rapt_ref.c restatement) - stored as regression vectors and
@@ -196,13 +199,34 @@ def collator():
     np.savez_compressed(os.path.join(HERE, "collate.npz"), **out)
 
 
+def demo_kat():
+    """demo.ipynb:36-50 on the reference's own assets/demo.pkl with the reference's own utils functions."""
+    import pickle
+    with open("/root/reference/assets/demo.pkl", "rb") as fh:
+        demo = pickle.load(fh)
+    out = {"n": len(demo)}
+    for k, sbmt in enumerate(demo):
+        mel, f0, length = sbmt[2][0], sbmt[2][1], sbmt[2][2]
+        out["spk%d" % k], out["mel%d" % k], out["f0%d" % k], out["len%d" % k] = sbmt[0], mel, f0, length
+        mel_pad, len_pad = ref_utils.pad_seq_to_2(mel[np.newaxis, :, :], 192)
+        f0_pad = np.pad(f0, (0, 192 - len(f0)), "constant", constant_values=(0, 0))
+        enc, idx = ref_utils.quantize_f0_numpy(f0_pad)
+        out["mel_pad%d" % k], out["len_pad%d" % k] = mel_pad, len_pad
+        out["enc_argmax%d" % k], out["enc_sum%d" % k], out["idx%d" % k] = enc.argmax(1), enc.sum(1), idx
+    np.savez_compressed(os.path.join(HERE, "demo_kat.npz"), **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["demo"]:
+        demo_kat()
+        sys.exit(0)
     if sys.argv[1:] == ["collate"]:          # only the loader vectors (the others are unchanged)
         collator()
         sys.exit(0)
     utils_kat()
     interp_lnr()
     collator()
+    demo_kat()
     # cfg1: one 3.000 s male utterance, speaker p226 (+ two more files of the same speaker so the
     # dither stream continuity and the L % 256 == 0 append path are pinned)
     pipeline("pipeline_p226.npz", [UttMeta("p226", "M", 0, 48000, 226000),

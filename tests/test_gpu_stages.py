@@ -361,3 +361,19 @@ def test_collator_golden_on_gpu(fe, tmp_path, golden_dir):
     for got, name in zip(batch, ("melsp", "spk_emb", "pitch", "len_org")):
         assert got.is_cuda and got.cpu().numpy().dtype == g[name].dtype
         assert np.array_equal(got.cpu().numpy(), g[name]), name
+
+
+def test_demo_notebook_inputs(fe, golden_dir):
+    """demo.ipynb:36-50 on the reference's own assets/demo.pkl (real VCTK features made by the original
+    pipeline): utils.pad_seq_to_2 + utils.quantize_f0_numpy give what the reference's utils give."""
+    from speechsplit_b200 import utils
+    g = np.load(os.path.join(golden_dir, "demo_kat.npz"))
+    for k in range(int(g["n"])):
+        f0, mel = g["f0%d" % k], g["mel%d" % k]
+        mel_pad, len_pad = utils.pad_seq_to_2(mel[np.newaxis, :, :], 192)
+        f0_pad = np.pad(f0, (0, 192 - len(f0)), "constant", constant_values=(0, 0))
+        enc, idx = utils.quantize_f0_numpy(f0_pad)
+        assert np.array_equal(mel_pad, g["mel_pad%d" % k]) and len_pad == int(g["len_pad%d" % k])
+        assert enc.dtype == np.float32 and enc.shape == (192, 257) and idx.dtype == np.int64
+        assert np.array_equal(idx, g["idx%d" % k])
+        assert np.array_equal(enc.argmax(1), g["enc_argmax%d" % k]) and np.array_equal(enc.sum(1), g["enc_sum%d" % k])

@@ -171,3 +171,16 @@ def test_collator_matches_reference(golden_dir):
     assert [m[0] for m in meta] == [str(x) for x in g["meta_speakers"]]
     assert np.array_equal(np.stack([m[1] for m in meta]), g["meta_emb"])
     assert ["|".join(m[2:]) for m in meta] == [str(x) for x in g["meta_files"]]
+
+
+def test_demo_asset_quantisation_matches_reference(golden_dir):
+    """The two real normalised-F0 tracks of the reference's assets/demo.pkl (outputs of the original pipeline
+    with the real pysptk) through the oracle's quantize_f0_numpy == through the reference's (demo.ipynb:36-50)."""
+    g = np.load(os.path.join(golden_dir, "demo_kat.npz"))
+    for k in range(int(g["n"])):
+        f0 = g["f0%d" % k]
+        f0_pad = np.pad(f0, (0, 192 - len(f0)), "constant", constant_values=(0, 0))
+        enc, idx = rp.quantize_f0_numpy(f0_pad)
+        assert np.array_equal(idx, g["idx%d" % k])
+        assert np.array_equal(enc.argmax(1), g["enc_argmax%d" % k]) and np.array_equal(enc.sum(1), g["enc_sum%d" % k])
+        assert (idx[:len(f0)] > 0).sum() > 30 and np.all(idx[len(f0):] == 0)      # voiced frames exist; padding is bin 0
