@@ -474,6 +474,10 @@ def run_ours(args):
                 "traffic": None, "frames_per_launch": T, "bytes_per_frame": BYTES_PER_FRAME,
                 "launch_ms": stft_ms, "fft_tflops_nominal": T * FLOP_PER_FRAME_FFT / (stft_ms * 1e-3) / 1e12,
                 "note": "issue / shared-memory bound, not HBM bound (DESIGN.md 5): 1344 B/frame vs ~790 warp instructions and 322 shared-memory wavefronts"}
+    # the binding roof of this kernel is FP32 issue, so that fraction is reported beside the HBM one
+    # (70.6 TFLOP/s = the FMA rate measured with profiles/microbench/fp64_bench.cu on this pool's B200s)
+    roofline["fp32_peak_tflops"] = 70.6
+    roofline["fft_frac_of_fp32_peak"] = roofline["fft_tflops_nominal"] / 70.6
     tr = os.path.join(ROOT, "profiles", "stft_traffic.json")
     if os.path.exists(tr):
         try:
