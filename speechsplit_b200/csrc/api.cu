@@ -427,8 +427,12 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
 
     // the dither stream is independent of the signal until the very last filtfilt kernel: generate
     // it on a side stream while the forward / backward-local passes run
+    // Production path: the generator leaves the finished dither term as float (4 bytes per sample).  The
+    // validation paths - sequential filter mode, or a caller asking for the fp64 wav - keep the raw word
+    // pairs and convert in the consumer, bit for bit numpy's doubles.
+    const bool dith_f32 = ctx->cfg.filtfilt_mode != 1 && !o->wav64;
     mark(ctx, ST_RAND);
-    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux))) return rc;
+    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux, dith_f32))) return rc;
     mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
@@ -440,7 +444,8 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     fo.wav = o->wav;
     fo.wav64 = o->wav64;
     fo.dith_ready = ctx->ev_join;
-    fo.dith_raw = true;
+    fo.dith_raw = !dith_f32;
+    fo.dith_f32 = dith_f32;
     if ((rc = filtfilt_run(ctx, x_dev, dtype, b->sample_offsets, fix.data(), n, fo))) return rc;
     mark(ctx, ST_EDGES);
     if ((rc = fill_reflect_edges(ctx, wavp, d_seg, d_fix, n))) return rc;

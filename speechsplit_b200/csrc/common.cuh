@@ -171,6 +171,7 @@ struct FiltOut {
     double *y = nullptr;             // filtfilt output (may be null when fused outputs requested)
     const double *dith = nullptr;    // dither stream (fixed offsets); wav = y*0.96 + (U-0.5)*1e-6
     bool dith_raw = false;           // dith holds raw MT19937 word pairs (mt_convert.cuh), not doubles
+    bool dith_f32 = false;           // dith holds the finished term float((U - 0.5) * 1e-6), 4 bytes per sample
     float *wavp = nullptr;           // padded layout base
     const int64_t *seg_off_dev = nullptr;
     float *wav = nullptr;            // flat f32 [fixed offsets]
@@ -185,8 +186,9 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
 // launch_on: nullptr / ctx->stream = public path (doubles out); ctx->aux = side stream, raw word pairs
 // out, ordering handled inside (waits for ev_dith_free and ev_mt_go: starts beside the previous call's
 // stationarity kernel).
+// dither_f32 (side-stream path only): float((U - 0.5) * cfg.dither_scale) out instead of raw word pairs.
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
-             int n, double *u_dev, cudaStream_t launch_on = nullptr);
+             int n, double *u_dev, cudaStream_t launch_on = nullptr, bool dither_f32 = false);
 
 int init_rapt(ssfe_ctx *ctx);
 void free_rapt(ssfe_ctx *ctx);

@@ -49,7 +49,9 @@ struct FiltConsts {
 
 struct FiltParams {
     const void *x;                // input samples (pass 1) or nullptr
-    const double *y1;             // forward result over the extended signal (pass 2 input)
+    const double *y1;             // forward result over the extended signal (pass 2 input), sequential mode
+    const float *y1f;             // the same for the tiled kernels: stored as float (see filt_tile_kernel)
+    float *y1f_out;
     const int64_t *in_off;        // [n+1] raw input offsets
     const int64_t *fix_off;       // [n+1] fixed (post-append) offsets
     const int *chunk_off;         // [n+1] prefix of chunk counts
@@ -65,6 +67,7 @@ struct FiltParams {
     double *wav64;
     double *y1_out;               // forward pass output (extended)
     int dith_raw;                 // dith holds raw MT19937 word pairs
+    int dith_f32;                 // dith holds float((U - 0.5) * 1e-6), already scaled (mt_convert.cuh)
     double *bpart;                // [n_chunks][2][5] (filtfilt_mode 2) partial backward states from the forward final pass
 };
 
@@ -155,9 +158,14 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
                 if (nidx >= 0 && nidx < Lf) {
                     if (p.y) p.y[fbase + nidx] = y;
                     if (p.dith) {
-                        const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(p.dith)[fbase + nidx])
-                                                     : p.dith[fbase + nidx];
-                        const double d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
+                        double d;
+                        if (p.dith_f32) {
+                            d = static_cast<double>(reinterpret_cast<const float *>(p.dith)[fbase + nidx]);
+                        } else {
+                            const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(p.dith)[fbase + nidx])
+                                                         : p.dith[fbase + nidx];
+                            d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
+                        }
                         const double w = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
                         if (p.wav64) p.wav64[fbase + nidx] = w;
                         const float wf = static_cast<float>(w);
@@ -199,9 +207,9 @@ struct Df2tFused {
     }
 };
 
-template <int DTYPE, int PASS> struct RawType { using T = double; };
+template <int DTYPE, int PASS> struct RawType { using T = float; };      // pass 1 reads y1, stored as float
 template <> struct RawType<SSFE_I16, 0> { using T = short; };
-template <> struct RawType<SSFE_F32, 0> { using T = float; };
+template <> struct RawType<SSFE_F64, 0> { using T = double; };
 
 template <int DTYPE, int PASS, bool FINAL, bool EMIT = false>
 __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
@@ -241,9 +249,16 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
     } else {
         ff.z0 = ff.z1 = ff.z2 = ff.z3 = ff.z4 = 0.0;
     }
-    const double *y1 = p.y1 + ebase;
-    double *y1o = FINAL ? p.y1_out + ebase : nullptr;
-    const double *dith = (FINAL && PASS == 1 && p.dith) ? p.dith + fbase : nullptr;
+    // The forward result travels to the backward pass as FLOAT (8.4 instead of 16.7 GB written once and read
+    // twice for the VCTK-shaped corpus).  The backward pass then filters exactly that rounded signal - both its
+    // local and its final pass read the same floats, so chunk-entry states stay consistent to the last bit,
+    // which is what the ill-conditioned recurrence needs - and the rounding enters as input noise of
+    // <= 1.5e-8 through a filter of gain <= 1.  Measured against scipy (CPU simulation, tests): the result moves
+    // by <= 2.6e-7, the size of scipy's own fp64 round-off for this filter and inside the 1e-6 bar.
+    const float *y1 = (PASS == 1) ? p.y1f + ebase : nullptr;
+    float *y1o = (FINAL && PASS == 0) ? p.y1f_out + ebase : nullptr;
+    const float *dith = (FINAL && PASS == 1 && p.dith && p.dith_f32) ? reinterpret_cast<const float *>(p.dith) + fbase : nullptr;
+    const double *dith_gen = (FINAL && PASS == 1 && p.dith && !p.dith_f32) ? p.dith + fbase : nullptr;
     float *wavp = (FINAL && PASS == 1 && p.wavp) ? p.wavp + p.seg_off[u] + kHalfPad : nullptr;
     // ---- load machinery -------------------------------------------------------------------------------
     // (For 16-bit input a tile is one contiguous 16 KB run; fetching it with a single TMA bulk copy into
@@ -286,13 +301,13 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
             }
         } else {
             if (fast_path) {
-                const double *ys = y1 + (M - 1 - js - lane);         // reversed: row r is kChunk samples earlier
+                const float *ys = y1 + (M - 1 - js - lane);          // reversed: row r is kChunk samples earlier
 #pragma unroll
-                for (int r = 0; r < 32; ++r) raw[r] = static_cast<RawT>(ys[-r * kChunk]);
+                for (int r = 0; r < 32; ++r) raw[r] = ys[-r * kChunk];
             } else {
 #pragma unroll
                 for (int r = 0; r < 32; ++r)
-                    raw[r] = static_cast<RawT>(y1[min(max(M - 1 - (js + r * kChunk + lane), 0), M - 1)]);
+                    raw[r] = y1[min(max(M - 1 - (js + r * kChunk + lane), 0), M - 1)];
             }
         }
     };
@@ -344,7 +359,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
             if (FINAL && EMIT) {
 #pragma unroll 4
                 for (int i = 0; i < cnt; ++i) {
-                    const double y = f.step(row[i]);
+                    // the backward pass filters the float-rounded forward result: its states must be sums over
+                    // exactly those values
+                    const double y = static_cast<double>(static_cast<float>(f.step(row[i])));
                     row[i] = y;
                     const int ig = sub * kTileW + i;
                     if (ig < dsplit) {
@@ -372,50 +389,42 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
             if (PASS == 1) {
                 // all 32 row segments map to output samples (none in the 18-sample pads)
                 const int n_hi = M - 1 - kPadLen - jsub, n_lo = n_hi - 31 * kChunk - (kTileW - 1);
-                fast_out = fast && n_lo >= 0 && n_hi < Lf && dith && p.dith_raw && wavp && !p.y && !p.wav && !p.wav64;
+                fast_out = fast && n_lo >= 0 && n_hi < Lf && dith && wavp && !p.y && !p.wav && !p.wav64;
             }
             if (fast_out && PASS == 0) {
 #pragma unroll
-                for (int r = 0; r < 32; ++r) y1o[jsub + r * kChunk + lane] = tl[r * kTileStride + lane];
+                for (int r = 0; r < 32; ++r) y1o[jsub + r * kChunk + lane] = static_cast<float>(tl[r * kTileStride + lane]);
             } else if (fast_out) {
-                // production path of the backward pass: wav = y * 0.96 + (U - 0.5) * 1e-06 -> f32 segment.
-                // The dither loads below are the kernel's largest stall (55 % of the samples).  Staging
-                // them with cp.async (8 KB of shared memory per warp) during the recurrence was
-                // measured: 3 CTAs per SM instead of 4, and the pass got 4.5 ms SLOWER on the full corpus.
+                // production path of the backward pass: wav = y * 0.96 + (U - 0.5) * 1e-06 -> f32 segment; the
+                // dither term arrives finished, as float (mt_walk_kernel<true>).  These loads were the kernel's
+                // largest stall when they were 8-byte raw word pairs (55 % of the samples); staging them with
+                // cp.async (8 KB of shared memory per warp) during the recurrence was measured then: 3 CTAs per SM
+                // instead of 4, and the pass got 4.5 ms SLOWER on the full corpus.
                 const int n0 = M - 1 - kPadLen - jsub - lane;
-                const uint2 *dr = reinterpret_cast<const uint2 *>(dith) + n0;
+                const float *dr = dith + n0;
+                float dv[32];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint2 raw[16];
+                for (int r = 0; r < 32; ++r) dv[r] = dr[-r * kChunk];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) raw[r] = dr[-(16 * h + r) * kChunk];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const double y = tl[(16 * h + r) * kTileStride + lane];
-                        const double d = __dmul_rn(__dsub_rn(mt_raw_to_double(raw[r]), 0.5), c_filt.dither_scale);
-                        wavp[n0 - (16 * h + r) * kChunk] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), d));
-                    }
+                for (int r = 0; r < 32; ++r) {
+                    const double y = tl[r * kTileStride + lane];
+                    wavp[n0 - r * kChunk] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(dv[r])));
                 }
-            } else if (PASS == 1 && dith && p.dith_raw && wavp && !p.y && !p.wav && !p.wav64) {
-                // edge tile of the production path: same combine, dither words fetched together
-                const uint2 *d2 = reinterpret_cast<const uint2 *>(dith);
+            } else if (PASS == 1 && dith && wavp && !p.y && !p.wav && !p.wav64) {
+                // edge tile of the production path: same combine, dither terms fetched together
+                float dv[32];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint2 dr[16];
+                for (int r = 0; r < 32; ++r) {
+                    const int nidx = M - 1 - kPadLen - (jsub + r * kChunk + lane);
+                    dv[r] = dith[min(max(nidx, 0), Lf - 1)];
+                }
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const int nidx = M - 1 - kPadLen - (jsub + (16 * h + r) * kChunk + lane);
-                        dr[r] = d2[min(max(nidx, 0), Lf - 1)];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const int j = jsub + (16 * h + r) * kChunk + lane;
-                        const int nidx = M - 1 - kPadLen - j;
-                        if (16 * h + r < rows && j < M && nidx >= 0 && nidx < Lf) {
-                            const double y = tl[(16 * h + r) * kTileStride + lane];
-                            const double d = __dmul_rn(__dsub_rn(mt_raw_to_double(dr[r]), 0.5), c_filt.dither_scale);
-                            wavp[nidx] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), d));
-                        }
+                for (int r = 0; r < 32; ++r) {
+                    const int j = jsub + r * kChunk + lane;
+                    const int nidx = M - 1 - kPadLen - j;
+                    if (r < rows && j < M && nidx >= 0 && nidx < Lf) {
+                        const double y = tl[r * kTileStride + lane];
+                        wavp[nidx] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(dv[r])));
                     }
                 }
             } else {
@@ -424,14 +433,19 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
                     if (j >= M) continue;
                     const double y = tl[r * kTileStride + lane];
                     if (PASS == 0) {
-                        y1o[j] = y;
+                        y1o[j] = static_cast<float>(y);
                     } else {
                         const int nidx = M - 1 - kPadLen - j;
                         if (nidx >= 0 && nidx < Lf) {
                             if (p.y) p.y[fbase + nidx] = y;
-                            if (dith) {
-                                const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(dith)[nidx]) : dith[nidx];
-                                const double d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
+                            if (dith || dith_gen) {
+                                double d;
+                                if (dith) {
+                                    d = static_cast<double>(dith[nidx]);
+                                } else {
+                                    const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(dith_gen)[nidx]) : dith_gen[nidx];
+                                    d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
+                                }
                                 const double wv = __dadd_rn(__dmul_rn(y, c_filt.wav_scale), d);
                                 if (p.wav64) p.wav64[fbase + nidx] = wv;
                                 const float wf = static_cast<float>(wv);
@@ -548,7 +562,7 @@ __global__ void __launch_bounds__(kCarryThreads) filt_carry_kernel(const FiltPar
         const int64_t M = Lf + 2 * kPadLen;
         const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
         if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
-        else x0 = p.y1[ebase + M - 1];
+        else x0 = p.y1f ? static_cast<double>(p.y1f[ebase + M - 1]) : p.y1[ebase + M - 1];
     }
     const int nmax = __reduce_max_sync(0xffffffffu, nc);
     const int rr = min(r, 4);
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_warp_kernel(const
     const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
     double x0;
     if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
-    else x0 = p.y1[ebase + M - 1];
+    else x0 = p.y1f ? static_cast<double>(p.y1f[ebase + M - 1]) : p.y1[ebase + M - 1];
     dd z0[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) z0[i] = {__dmul_rn(c_filt.zi[i], x0), 0.0};
@@ -714,7 +728,8 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     else if (fused_states) filt_tile_kernel<DTYPE, 0, true, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
-    p.y1 = p.y1_out;
+    if (sequential) p.y1 = p.y1_out;
+    else p.y1f = p.y1f_out;
     if (fused_states) {
         filt_bstate_kernel<<<gc, kFiltThreads, 0, st>>>(p, nullptr);
         SSFE_LAUNCHED(ctx);
@@ -764,7 +779,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     chunk_off[n] = static_cast<int>(chunks);
     tile_off[n] = static_cast<int>(tiles);
     const int64_t ext_total = fix_off_host[n] + static_cast<int64_t>(n) * 2 * kPadLen;
-    int rc = ensure(ctx, ctx->ws.y1, ext_total * sizeof(double));
+    int rc = ensure(ctx, ctx->ws.y1, ext_total * (sequential ? sizeof(double) : sizeof(float)));
     if (rc) return rc;
     rc = ensure(ctx, ctx->ws.carry, (fused_states ? 4 : 2) * chunks * 5 * sizeof(double));
     if (rc) return rc;
@@ -797,11 +812,13 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.y = out.y;
     p.dith = out.dith;
     p.dith_raw = out.dith_raw ? 1 : 0;
+    p.dith_f32 = out.dith_f32 ? 1 : 0;
     p.wavp = out.wavp;
     p.seg_off = out.seg_off_dev;
     p.wav = out.wav;
     p.wav64 = out.wav64;
-    p.y1_out = static_cast<double *>(ctx->ws.y1.p);
+    p.y1_out = sequential ? static_cast<double *>(ctx->ws.y1.p) : nullptr;
+    p.y1f_out = sequential ? nullptr : static_cast<float *>(ctx->ws.y1.p);
     switch (dtype) {
     case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long, fused_states);
     case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long, fused_states);

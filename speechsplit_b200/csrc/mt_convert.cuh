@@ -23,4 +23,12 @@ __device__ __forceinline__ double mt_raw_to_double(uint2 raw)
     return (static_cast<double>(a) * 67108864.0 + static_cast<double>(b)) * (1.0 / 9007199254740992.0);   // exact
 }
 
+// The production path of ssfe_extract stores the dither term itself,  (U - 0.5) * 1e-06  (make_spect_f0.py:55),
+// rounded once more to float: 4 bytes per sample instead of 8 through HBM.  The term is <= 5e-7 in magnitude, so
+// the extra rounding is <= 3e-14 absolute - eight orders below one float ulp of the signal it is added to.
+__device__ __forceinline__ float mt_raw_to_dither_f32(uint2 raw, double scale)
+{
+    return static_cast<float>(__dmul_rn(__dsub_rn(mt_raw_to_double(raw), 0.5), scale));
+}
+
 }  // namespace ssfe

@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const Rap
         const int sub = lane >> 3, l8 = lane & 7;
         const int gq = g_tile + w + kCandWarps * sub;
         const int gc = min(gq, ut.n_fr - 1);                       // frames past the end: computed, not kept
-        float *cdb = s_cc[w] + 64 * sub;                           // [64] coarse window
-        double *cec = reinterpret_cast<double *>(s_db[w]) + 40 * sub;   // [40] lagged energy per lag
+        // (strides of 72 floats / 44 doubles, not 64 / 40: the four quarter-warps then start 8 banks apart
+        // instead of on the same bank - the plain layout made every access of this stage a 4-way conflict,
+        // a quarter of the kernel's shared-memory wavefronts in ncu)
+        float *cdb = s_cc[w] + 72 * sub;                           // [64] coarse window
+        double *cec = reinterpret_cast<double *>(s_db[w]) + 44 * sub;   // [40] lagged energy per lag
         float *ccc = s_pklc[w] + 40 * sub;                         // [40] coarse correlation
         float *cpk = s_pklc[w] + 160 + kCMax * sub;                // [20] peaks
         int *clc = reinterpret_cast<int *>(s_pklc[w] + 160 + 4 * kCMax) + kCMax * sub;   // [20] lags
