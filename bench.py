@@ -57,7 +57,6 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=None, help="utterances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--filtfilt-mode", type=int, default=0, help="0 = scan, 2 = EXPERIMENTAL fused backward states")
     ap.add_argument("--parity-utts", type=int, default=12)
     ap.add_argument("--workload", default="vctk", choices=["vctk", "longform", "single", "collate"],
                     help="vctk = BASELINE configs[1]/[2] (the bench line); longform = configs[3] (256 x 60 s); "
@@ -270,7 +269,7 @@ def run_ours(args):
 
     import torch
     import torch.distributed as dist
-    from speechsplit_b200 import FrontEnd, FrontEndConfig
+    from speechsplit_b200 import FrontEnd
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -284,7 +283,7 @@ def run_ours(args):
     audio_s_rank = float((off[-1]) / FS)
     audio_s_total = float(sum(m.length for m in metas) / FS)
 
-    fe = FrontEnd(local, FrontEndConfig(filtfilt_mode=args.filtfilt_mode))
+    fe = FrontEnd(local)
     fix, fr = fe.plan(off)
     T = int(fr[-1])
     outs = dict(mel=torch.empty((T, 80), dtype=torch.float32, device=dev),

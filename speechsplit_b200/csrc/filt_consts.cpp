@@ -71,27 +71,3 @@ extern "C" void ssfe_filt_power_table_dd(const double *a6, int base, int count, 
         std::memcpy(P, T, sizeof(P));
     }
 }
-
-// v[j] = A^j g for j < count, g[i] = b[i+1] - a[i+1] b[0]: the state a unit sample leaves behind j steps later
-// (zero-state DF2T).  |v[j]| stays below 0.25 although |A^j| reaches 1e8, so it is iterated in 113 bits
-// and rounded once.  out holds count * 5 doubles.
-extern "C" void ssfe_filt_impulse_states(const double *a6, const double *b6, int count, double *out)
-{
-    typedef __float128 q;
-    q A[25], v[5], t[5];
-    for (int i = 0; i < 25; ++i) A[i] = 0;
-    for (int i = 0; i < 5; ++i) {
-        A[i * 5 + 0] = -(q)a6[i + 1];
-        if (i + 1 < 5) A[i * 5 + i + 1] = 1;
-        v[i] = (q)b6[i + 1] - (q)a6[i + 1] * (q)b6[0];
-    }
-    for (int j = 0; j < count; ++j) {
-        for (int i = 0; i < 5; ++i) out[j * 5 + i] = (double)v[i];
-        for (int i = 0; i < 5; ++i) {
-            q acc = 0;
-            for (int k = 0; k < 5; ++k) acc += A[i * 5 + k] * v[k];
-            t[i] = acc;
-        }
-        std::memcpy(v, t, sizeof(v));
-    }
-}

@@ -29,7 +29,6 @@ namespace ssfe {
 
 extern "C" void ssfe_filt_power_dd(const double *a6, int power, double *hi25, double *lo25);   // filt_consts.cpp
 extern "C" void ssfe_filt_power_table_dd(const double *a6, int base, int count, double *out);
-extern "C" void ssfe_filt_impulse_states(const double *a6, const double *b6, int count, double *out);
 
 constexpr int kChunk = 256;
 constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
@@ -68,13 +67,9 @@ struct FiltParams {
     double *y1_out;               // forward pass output (extended)
     int dith_raw;                 // dith holds raw MT19937 word pairs
     int dith_f32;                 // dith holds float((U - 0.5) * 1e-6), already scaled (mt_convert.cuh)
-    double *bpart;                // [n_chunks][2][5] (filtfilt_mode 2) partial backward states from the forward final pass
 };
 
 __constant__ FiltConsts c_filt;
-// filtfilt_mode 2 (EXPERIMENTAL): A^j g, j < 256 - the weights with which the forward final pass sums the
-// backward pass's zero-state chunk finals while it has y1 in registers (profiles/microbench/filt_fused_states.py)
-__constant__ double c_bstate[kChunk][5];
 
 template <int DTYPE>
 __device__ __forceinline__ double load_sample(const void *x, int64_t i)
@@ -211,8 +206,8 @@ template <int DTYPE, int PASS> struct RawType { using T = float; };      // pass
 template <> struct RawType<SSFE_I16, 0> { using T = short; };
 template <> struct RawType<SSFE_F64, 0> { using T = double; };
 
-template <int DTYPE, int PASS, bool FINAL, bool EMIT = false>
-__global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
+template <int DTYPE, int PASS, bool FINAL>
+__global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
                                                                      int n_tiles, const int *__restrict__ tile_map)
 {
     __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
@@ -317,12 +312,6 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
         e0 = fixed_sample<DTYPE>(p.x, xbase, L, 0);
         e1 = fixed_sample<DTYPE>(p.x, xbase, L, Lf - 1);
     }
-    // EMIT: the backward pass cuts the reversed signal into chunks from ITS start, i.e. at forward positions
-    // congruent to d = M mod 256.  Samples i >= d of this forward chunk belong to one backward chunk (weight
-    // A^(i-d) g), samples i < d to the next one (weight A^(i+256-d) g); the two partial sums are added by
-    // filt_bstate_kernel.  d and i are uniform across the warp, so the weights are constant-bank broadcasts.
-    const int dsplit = M % kChunk;
-    double aL0 = 0.0, aL1 = 0.0, aL2 = 0.0, aL3 = 0.0, aL4 = 0.0, aH0 = 0.0, aH1 = 0.0, aH2 = 0.0, aH3 = 0.0, aH4 = 0.0;
     issue(0, is_fast(0));
     for (int sub = 0; sub < kChunk / kTileW; ++sub) {
         const int jsub = jt + sub * kTileW;
@@ -356,25 +345,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
             const int left = M - (j0 + sub * kTileW);                        // may be <= 0 past the end
             const int cnt = left < kTileW ? left : kTileW;
             double *row = tl + lane * kTileStride;
-            if (FINAL && EMIT) {
-#pragma unroll 4
-                for (int i = 0; i < cnt; ++i) {
-                    // the backward pass filters the float-rounded forward result: its states must be sums over
-                    // exactly those values
-                    const double y = static_cast<double>(static_cast<float>(f.step(row[i])));
-                    row[i] = y;
-                    const int ig = sub * kTileW + i;
-                    if (ig < dsplit) {
-                        const double *cf = c_bstate[ig + kChunk - dsplit];
-                        aL0 = fma(cf[0], y, aL0); aL1 = fma(cf[1], y, aL1); aL2 = fma(cf[2], y, aL2);
-                        aL3 = fma(cf[3], y, aL3); aL4 = fma(cf[4], y, aL4);
-                    } else {
-                        const double *cf = c_bstate[ig - dsplit];
-                        aH0 = fma(cf[0], y, aH0); aH1 = fma(cf[1], y, aH1); aH2 = fma(cf[2], y, aH2);
-                        aH3 = fma(cf[3], y, aH3); aH4 = fma(cf[4], y, aH4);
-                    }
-                }
-            } else if (FINAL) {
+            if (FINAL) {
 #pragma unroll 4
                 for (int i = 0; i < cnt; ++i) row[i] = f.step(row[i]);
             } else {
@@ -463,34 +434,6 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 && !EMIT ? 5 : 4))
         double *s = p.state + g * 5;
         s[0] = ff.z0; s[1] = ff.z1; s[2] = ff.z2; s[3] = ff.z3; s[4] = ff.z4;
     }
-    if (FINAL && EMIT && have) {
-        double *s = p.bpart + g * 10;
-        s[0] = aL0; s[1] = aL1; s[2] = aL2; s[3] = aL3; s[4] = aL4;
-        s[5] = aH0; s[6] = aH1; s[7] = aH2; s[8] = aH3; s[9] = aH4;
-    }
-}
-
-// filtfilt_mode 2: zero-state final of backward chunk k (reversed samples [256 k, 256 k + 256), i.e. forward
-// positions [p, p + 256) with p = M - 256 (k + 1)) = the "high" partial of the forward chunk that holds p plus
-// the "low" partial of the next one.  Writes the array the backward carry reads (the last backward chunk's
-// final is never consumed, like in the local pass).
-__global__ void filt_bstate_kernel(const FiltParams p, const int *__restrict__ chunk_map)
-{
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.n_chunks) return;
-    const int u = chunk_map ? chunk_map[g] : find_segment(p.chunk_off, p.n, g);
-    const int k = g - p.chunk_off[u];
-    const int nch = p.chunk_off[u + 1] - p.chunk_off[u];
-    if (k >= nch - 1) return;
-    const int M = static_cast<int>(p.fix_off[u + 1] - p.fix_off[u]) + 2 * kPadLen;
-    const int pos = M - kChunk * (k + 1);                  // > 0 for k <= nch - 2
-    const int c1 = pos / kChunk;
-    const double *hi = p.bpart + (static_cast<int64_t>(p.chunk_off[u]) + c1) * 10 + 5;
-    const double *lo = p.bpart + (static_cast<int64_t>(p.chunk_off[u]) + c1 + 1) * 10;
-    const bool has_lo = (M % kChunk) != 0;                 // aligned: the forward chunk is the backward chunk
-    double *s = p.state + static_cast<int64_t>(g) * 5;
-#pragma unroll
-    for (int r = 0; r < 5; ++r) s[r] = has_lo ? __dadd_rn(hi[r], lo[r]) : hi[r];
 }
 
 // ---- double-double helpers for the carry -------------------------------------------------------
@@ -707,7 +650,7 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 
 template <int DTYPE>
 static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready,
-                          const int *tile_off, int n_tiles, const int *tile_map, bool any_long, bool fused_states)
+                          const int *tile_off, int n_tiles, const int *tile_map, bool any_long)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
@@ -725,15 +668,11 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
         SSFE_LAUNCHED(ctx);
     }
     if (sequential) filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
-    else if (fused_states) filt_tile_kernel<DTYPE, 0, true, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     if (sequential) p.y1 = p.y1_out;
     else p.y1f = p.y1f_out;
-    if (fused_states) {
-        filt_bstate_kernel<<<gc, kFiltThreads, 0, st>>>(p, nullptr);
-        SSFE_LAUNCHED(ctx);
-    } else if (!sequential) {
+    if (!sequential) {
         filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
         SSFE_LAUNCHED(ctx);
     }
@@ -756,7 +695,6 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
 {
     if (n == 0) return SSFE_OK;
     const bool sequential = ctx->cfg.filtfilt_mode == 1;
-    const bool fused_states = ctx->cfg.filtfilt_mode == 2;      // EXPERIMENTAL, see filt_bstate_kernel
     std::vector<int> chunk_off(n + 1), tile_off(n + 1);
     int64_t chunks = 0, max_m = 0, tiles = 0;
     bool any_long = false;
@@ -781,7 +719,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     const int64_t ext_total = fix_off_host[n] + static_cast<int64_t>(n) * 2 * kPadLen;
     int rc = ensure(ctx, ctx->ws.y1, ext_total * (sequential ? sizeof(double) : sizeof(float)));
     if (rc) return rc;
-    rc = ensure(ctx, ctx->ws.carry, (fused_states ? 4 : 2) * chunks * 5 * sizeof(double));
+    rc = ensure(ctx, ctx->ws.carry, 2 * chunks * 5 * sizeof(double));
     if (rc) return rc;
 
     FiltParams p;
@@ -808,7 +746,6 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.chunk_len = sequential ? static_cast<int>(std::min<int64_t>(max_m, 0x7fffffff)) : kChunk;
     p.state = static_cast<double *>(ctx->ws.carry.p);
     p.zin = p.state + chunks * 5;
-    p.bpart = fused_states ? p.zin + chunks * 5 : nullptr;
     p.y = out.y;
     p.dith = out.dith;
     p.dith_raw = out.dith_raw ? 1 : 0;
@@ -820,9 +757,9 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.y1_out = sequential ? static_cast<double *>(ctx->ws.y1.p) : nullptr;
     p.y1f_out = sequential ? nullptr : static_cast<float *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long, fused_states);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long, fused_states);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long, fused_states);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }
@@ -846,11 +783,6 @@ int init_filtfilt(ssfe_ctx *ctx)
     c.wav_scale = ctx->cfg.wav_scale;
     c.dither_scale = ctx->cfg.dither_scale;
     SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_filt, &c, sizeof(c)));
-    {
-        std::vector<double> bs(kChunk * 5);
-        ssfe_filt_impulse_states(c.a, c.b, kChunk, bs.data());
-        SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_bstate, bs.data(), bs.size() * sizeof(double)));
-    }
     return SSFE_OK;
 }
 

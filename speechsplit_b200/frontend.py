@@ -37,7 +37,7 @@ class FrontEndConfig:
     dither_scale: float = 1e-06
     ref_db: float = 16.0
     min_level: float = float(np.exp(-100 / 20 * np.log(10)))
-    filtfilt_mode: int = 0        # 1 = sequential validation mode, 2 = EXPERIMENTAL fused backward states
+    filtfilt_mode: int = 0        # 1 = sequential validation mode
     mel_basis: Optional[np.ndarray] = field(default=None, repr=False)
 
 

@@ -108,35 +108,3 @@ def test_fft_core_host_emulation(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     err = float(r.stdout.split("=")[1].split()[0])
     assert err <= 3e-6, r.stdout
-
-
-def test_fused_state_weights_and_chunk_algebra(lib):
-    """EXPERIMENTAL filtfilt_mode 2, host side: ssfe_filt_impulse_states gives A^j g (|.| < 0.25), and the
-    partition the kernels use - per forward chunk a "low" sum (samples i < d, weight index i + 256 - d) and a
-    "high" sum (i >= d, index i - d), d = M mod 256; backward chunk k = high[c1] + low[c1 + 1] with
-    c1 = (M - 256 (k + 1)) // 256 - reproduces the zero-state finals of the backward local pass."""
-    from scipy import signal
-    b, a = signal.butter(5, 30 / 8000.0, btype="high")
-    out = np.zeros(256 * 5)
-    fn = lib.ssfe_filt_impulse_states
-    fn.restype = None
-    fn(a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), 256, out.ctypes.data_as(ctypes.c_void_p))
-    coef = out.reshape(256, 5)
-    assert 0.2 < np.abs(coef).max() < 0.25
-    assert np.allclose(coef[0], b[1:] - a[1:] * b[0], rtol=0, atol=1e-14)
-    rng = np.random.default_rng(1)
-    for M in (48036, 20047, 256 * 7, 300):
-        y1 = rng.standard_normal(M) * 0.2
-        nch, d = -(-M // 256), M % 256
-        lo, hi = np.zeros((nch, 5)), np.zeros((nch, 5))
-        for c in range(nch):
-            seg = y1[256 * c: 256 * c + 256]
-            i = np.arange(len(seg))
-            lo[c] = (coef[(i + 256 - d) % 256][i < d] * seg[i < d, None]).sum(0)
-            hi[c] = (coef[(i - d) % 256][i >= d] * seg[i >= d, None]).sum(0)
-        r = y1[::-1]
-        for k in range(nch - 1):
-            c1 = (M - 256 * (k + 1)) // 256
-            s = hi[c1] + (lo[c1 + 1] if d else 0.0)
-            _, zf = signal.lfilter(b, a, r[256 * k: 256 * k + 256], zi=np.zeros(5))
-            assert np.abs(s - zf).max() < 2e-6, (M, k)      # lfilter's own fp64 round-off is ~5e-7 here

@@ -348,15 +348,3 @@ def test_extract_large_corpus_properties(fe):
         total += b.size
     assert worst <= 1e-4, worst
     assert same >= 0.999 * total, (same, total)
-
-
-def test_extract_golden_fused_states_mode(golden_dir):
-    """EXPERIMENTAL filtfilt_mode 2 through the whole loop: same gates as the scan mode."""
-    from speechsplit_b200 import FrontEnd, FrontEndConfig
-    f2 = FrontEnd(0, FrontEndConfig(filtfilt_mode=2))
-    try:
-        pcm, meta = _golden_batch(golden_dir, NAMES)
-        res = _extract(f2, pcm, meta, WANT)
-        print(_check_against(res, meta, exact_f0=False))
-    finally:
-        f2.close()

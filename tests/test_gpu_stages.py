@@ -377,43 +377,3 @@ def test_demo_notebook_inputs(fe, golden_dir):
         assert enc.dtype == np.float32 and enc.shape == (192, 257) and idx.dtype == np.int64
         assert np.array_equal(idx, g["idx%d" % k])
         assert np.array_equal(enc.argmax(1), g["enc_argmax%d" % k]) and np.array_equal(enc.sum(1), g["enc_sum%d" % k])
-
-
-# ---- EXPERIMENTAL filtfilt_mode 2 (branch exp/filt-fused-states): backward chunk states emitted by the
-# forward final pass, no backward local pass over y1 ---------------------------------------------------
-@pytest.fixture(scope="module")
-def fe_fused():
-    from speechsplit_b200 import FrontEnd, FrontEndConfig
-    f = FrontEnd(0, FrontEndConfig(filtfilt_mode=2))
-    yield f
-    f.close()
-
-
-def test_filtfilt_fused_states_vs_scipy(fe, fe_fused):
-    xs = _filtfilt_cases()
-    rng = np.random.default_rng(12)
-    xs += [rng.standard_normal(256 * 7 - 36) * 0.1,        # M % 256 == 0: forward chunks == backward chunks
-           rng.standard_normal(300) * 0.1]                 # two chunks
-    x, off = _ragged(xs, np.float64)
-    y, fix = fe_fused.filtfilt(torch.from_numpy(x), off)
-    y0, _ = fe.filtfilt(torch.from_numpy(x), off)
-    y, y0 = y.cpu().numpy(), y0.cpu().numpy()
-    for i, xi in enumerate(xs):
-        ref = rp.highpass_filtfilt(rp.length_fixup(xi))
-        err = np.abs(y[fix[i]:fix[i + 1]] - ref).max()
-        print("utt %d (L=%d): fused %.2e  scan %.2e" % (i, len(xi), err, np.abs(y0[fix[i]:fix[i + 1]] - ref).max()))
-        assert err <= 1e-6, "utt %d (L=%d): %g" % (i, len(xi), err)
-
-
-def test_filtfilt_fused_states_long_form_and_dtypes(fe_fused):
-    rng = np.random.default_rng(2)
-    x = 0.1 * rng.standard_normal(960000) + 0.2 * np.sin(np.arange(960000) * 2 * np.pi * 95 / 16000)
-    y, fix = fe_fused.filtfilt(torch.from_numpy(x), [0, 960000])
-    ref = rp.highpass_filtfilt(rp.length_fixup(x))
-    assert fix[-1] == 960001 and np.abs(y.cpu().numpy() - ref).max() <= 1e-6
-    pcm = synth_batch(make_manifest(1, 2, seed=5))
-    x64, off = _ragged([pcm_to_float64(p) for p in pcm], np.float64)
-    y64, _ = fe_fused.filtfilt(torch.from_numpy(x64), off)
-    y32, _ = fe_fused.filtfilt(torch.from_numpy(x64.astype(np.float32)), off)
-    y16, _ = fe_fused.filtfilt(torch.cat(pcm), off)
-    assert torch.equal(y64, y32) and torch.equal(y64, y16)
