@@ -75,7 +75,7 @@ def _check_against(res, meta, exact_f0):
         # one-hot consistent with bins: exactly quantize_f0_numpy's encoding
         enc = onehot[fo[i]:fo[i + 1]]
         assert enc.shape == (len(g_bins), 257) and np.array_equal(enc.argmax(1), g_bins) and np.all(enc.sum(1) == 1)
-        if m["wav"] is not None:
+        if m["wav"] is not None and "wav64" in res:
             w = res["wav64"].cpu().numpy()[fx[i]:fx[i + 1]]
             assert np.abs(w - m["wav"]).max() <= (1e-12 if exact_f0 else 1e-6)
     assert worst_mel <= 1e-4, worst_mel
@@ -92,6 +92,37 @@ def test_extract_golden_scan_mode(fe, golden_dir):
     pcm, meta = _golden_batch(golden_dir, NAMES)
     res = _extract(fe, pcm, meta, WANT)
     _check_against(res, meta, exact_f0=False)
+
+
+def test_extract_golden_production_path(fe, golden_dir):
+    """Without the fp64 wav among the outputs ssfe_extract takes its production path: the dither term travels
+    as float (mt_walk_kernel<true>) and the backward filter pass writes the padded f32 segments directly."""
+    pcm, meta = _golden_batch(golden_dir, NAMES)
+    res = _extract(fe, pcm, meta, ("mel", "f0_norm", "f0_raw", "bins", "onehot"))
+    _check_against(res, meta, exact_f0=False)
+    ref = _extract(fe, pcm, meta, WANT)
+    # float dither vs raw word pairs: the f32 wav may differ in the last bit on a few samples per million, far
+    # below what moves a mel value
+    assert (res["mel"] - ref["mel"]).abs().max().item() <= 2e-6
+    assert (res["bins"] == ref["bins"]).float().mean().item() >= 0.999
+
+
+def test_extract_long_form_60s_whole_loop(fe):
+    """BASELINE configs[3] shape: the whole loop on 60.000 s utterances (L = 960 000 -> 960 001 by the :52-53
+    append, 3 751 frames; the filter carry takes the warp-scan path, the Viterbi pass 3 751 steps), one male and
+    one female speaker, against the oracle - same gates as everywhere."""
+    metas = make_manifest(2, 1, seed=4, fixed_len=960000)
+    pcm = [p.numpy() for p in synth_batch(metas)]
+    meta = []
+    for m, p in zip(metas, pcm):
+        S, f0n, st = rp.extract_utterance(pcm_to_float64(p), m.gender, RandomState(m.spk_id), want_stages=True)
+        assert S.shape == (3751, 80)
+        meta.append(dict(spk=m.spk, gender=m.gender, skip=0, S=S, f0=st["f0_rapt"], f0n=f0n,
+                         bins=rp.quantize_f0_numpy(f0n)[1], wav=None))
+    res = _extract(fe, pcm, meta, ("mel", "f0_norm", "f0_raw", "bins", "onehot"))
+    assert res["frame_offsets"][-1] == 2 * 3751 and res["fixed_offsets"][-1] == 2 * 960001
+    worst_mel, frac, cents = _check_against(res, meta, exact_f0=False)
+    print("60 s whole loop: mel %.2e  identical bins %.5f  worst F0 %.3f cent" % (worst_mel, frac, cents))
 
 
 def test_extract_golden_sequential_mode_is_exact(fe_seq, golden_dir):

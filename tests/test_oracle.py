@@ -184,3 +184,20 @@ def test_demo_asset_quantisation_matches_reference(golden_dir):
         assert np.array_equal(idx, g["idx%d" % k])
         assert np.array_equal(enc.argmax(1), g["enc_argmax%d" % k]) and np.array_equal(enc.sum(1), g["enc_sum%d" % k])
         assert (idx[:len(f0)] > 0).sum() > 30 and np.all(idx[len(f0):] == 0)      # voiced frames exist; padding is bin 0
+
+
+def test_torch_eager_restatement_matches_reference_vectors(golden_dir, kat):
+    """oracle/torch_eager_ref.py (the reference's own GPU-side eager ops, bench.py's opponent for configs[4]) on
+    the CPU: InterpLnr vs the output of the reference's module for the captured draws, quantize_f0_torch vs the
+    vectors the reference's utils.py produced."""
+    import torch
+    from oracle.torch_eager_ref import interp_lnr_eager, quantize_f0_eager
+    z = np.load(os.path.join(golden_dir, "interp_lnr.npz"))
+    for k in range(int(z["n"])):
+        x = torch.from_numpy(z["x%d" % k])
+        y = interp_lnr_eager(x, torch.from_numpy(z["len_seq%d" % k]), max_len_pad=z["y%d" % k].shape[1],
+                             draws=(torch.from_numpy(z["scales%d" % k]), torch.from_numpy(z["len_seg%d" % k])))
+        assert np.array_equal(y.numpy(), z["y%d" % k]), k
+    enc, idx = quantize_f0_eager(torch.from_numpy(kat["qt_in"]))
+    assert enc.dtype == torch.float32 and idx.dtype == torch.int64
+    assert np.array_equal(idx.numpy(), kat["qt_idx"]) and np.array_equal(enc.argmax(-1).numpy(), kat["qt_enc_argmax"])
