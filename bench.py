@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--parity-utts", default="all",
                     help="'all' = the oracle over every utterance of rank 0's shard (default), or a number of sampled utterances, 0 = none")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[0]/[3]/[4] legs of the default run")
+    ap.add_argument("--filtfilt-mode", type=int, default=0, help="diagnostics: 1 = sequential validation mode of the filter (one thread per utterance)")
     ap.add_argument("--workload", default="vctk", choices=["vctk", "longform", "single", "collate"],
                     help="vctk = BASELINE configs[1]/[2] (the bench line); longform = configs[3] (256 x 60 s); "
                          "single = configs[0] (one 3 s male utterance); collate = configs[4] (batch-16 training crops)")
@@ -500,7 +501,7 @@ def run_ours(args):
 
     import torch
     import torch.distributed as dist
-    from speechsplit_b200 import FrontEnd
+    from speechsplit_b200 import FrontEnd, FrontEndConfig
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -514,7 +515,7 @@ def run_ours(args):
     audio_s_rank = float((off[-1]) / FS)
     audio_s_total = float(sum(m.length for m in metas) / FS)
 
-    fe = FrontEnd(local)
+    fe = FrontEnd(local, FrontEndConfig(filtfilt_mode=args.filtfilt_mode))
     fix, fr = fe.plan(off)
     T = int(fr[-1])
     outs = dict(mel=torch.empty((T, 80), dtype=torch.float32, device=dev),
@@ -737,7 +738,7 @@ def _parity_job(job):
     unv = np.float32(-1e10)
     r = dict(frames=0, same_bins=0, utts=0, utts_with_diff=0, voicing_mismatch=0, mel_max=0.0, mel_over=0,
              cents_max=0.0, voiced_both=0, cents_over=0, f0_norm_max=0.0, audio_s=0.0,
-             hist=np.zeros(len(_HIST_EDGES) - 1, np.int64), worst=[])
+             hist=np.zeros(len(_HIST_EDGES) - 1, np.int64), worst=[], band_max=np.zeros(80), cells=[])
     for (idx, s0, s1, f0, f1, skip) in utts:
         while pos < skip:                      # advance the stream (bounded chunks)
             n = int(min(skip - pos, 1 << 22))
@@ -752,6 +753,10 @@ def _parity_job(job):
         r["hist"] += np.histogram(d, bins=_HIST_EDGES)[0]
         dm = float(d.max())
         r["mel_max"] = max(r["mel_max"], dm)
+        r["band_max"] = np.maximum(r["band_max"], d.max(axis=0))
+        if dm > 5e-5:
+            t, bnd = np.unravel_index(int(d.argmax()), d.shape)
+            r["cells"].append((dm, int(idx), int(t), int(bnd), float(S[t, bnd]), float(gm[t, bnd]), int(S.shape[0])))
         r["mel_over"] += int((d > 1e-4).sum())
         rb = rp.quantize_f0_numpy(f0n)[1]
         gb = np.asarray(bins[f0:f1])
@@ -817,8 +822,10 @@ def parity_sweep(mine, skips, x, off, fr, outs, which, per_task=40):
                voiced_both=0, audio_s=0.0)
     hist = np.zeros(len(_HIST_EDGES) - 1, np.int64)
     mel_max = cents_max = f0n_max = 0.0
-    worst = []
+    worst, cells, band_max = [], [], np.zeros(80)
     for r in res:
+        cells += r["cells"]
+        band_max = np.maximum(band_max, r["band_max"])
         for k in tot:
             tot[k] += r[k]
         hist += r["hist"]
@@ -840,6 +847,9 @@ def parity_sweep(mine, skips, x, off, fr, outs, which, per_task=40):
             "voicing_flag_mismatches": int(tot["voicing_mismatch"]),
             "f0_worst_cents_voiced_both": cents_max, "f0_frames_over_1_cent": int(tot["cents_over"]),
             "frames_voiced_in_both": int(tot["voiced_both"]), "f0_norm_max_abs": f0n_max,
+            "mel_max_abs_per_band": [float("%.3g" % v) for v in band_max],
+            "worst_mel_cells": [{"abs": a, "utt": b, "frame": c, "band": e, "ref": f, "got": g, "frames_in_utt": h}
+                                for a, b, c, e, f, g, h in sorted(cells, reverse=True)[:12]],
             "worst_utterances": [{"index": a, "different_bins": b, "mel_max_abs": c} for a, b, c in worst[:5]],
             "oracle_wall_s": wall, "oracle_audio_s_per_s": tot["audio_s"] / max(wall, 1e-9), "setup_s": t1 - t0,
             "gates": "mel <= 1e-4 abs; bins + voicing identical on >= 99.9 % of frames; F0 <= 1 cent where voiced in both",

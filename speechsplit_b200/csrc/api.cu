@@ -68,6 +68,9 @@ int stage_copy(ssfe_ctx *ctx, void *dst_dev, const void *src_pinned, size_t byte
 void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
 {
     const size_t need = (bytes + 255) / 256 * 256;
+    if (need > ctx->meta_cap || ctx->meta_used + need > ctx->meta_cap) {
+        if (flush_meta(ctx) != SSFE_OK) return nullptr;        // what is staged goes out before the arena moves or wraps
+    }
     if (need > ctx->meta_cap) {
         // grow: the old arena may still hold metadata of kernels that are queued or not even launched yet
         // (earlier uploads of the same call), so it is retired, not freed, until the context goes away
@@ -94,12 +97,20 @@ void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes)
     char *h = ctx->meta_host + ctx->meta_used;
     char *d = ctx->meta_dev + ctx->meta_used;
     memcpy(h, host, bytes);
-    if (stage_copy(ctx, d, h, bytes, ctx->stream) != SSFE_OK) {
-        set_error(ctx, SSFE_ERR_CUDA, "metadata upload failed");
-        return nullptr;
-    }
+    if (ctx->meta_pend_bytes == 0) ctx->meta_pend_off = ctx->meta_used;
     ctx->meta_used += need;
+    ctx->meta_pend_bytes = ctx->meta_used - ctx->meta_pend_off;
     return d;
+}
+
+int flush_meta(ssfe_ctx *ctx)
+{
+    if (ctx->meta_pend_bytes == 0) return SSFE_OK;
+    const size_t off = ctx->meta_pend_off, bytes = ctx->meta_pend_bytes;
+    ctx->meta_pend_bytes = 0;
+    if (stage_copy(ctx, ctx->meta_dev + off, ctx->meta_host + off, bytes, ctx->stream) != SSFE_OK)
+        return set_error(ctx, SSFE_ERR_CUDA, "metadata upload failed");
+    return SSFE_OK;
 }
 
 void mark(ssfe_ctx *ctx, int boundary)
@@ -218,9 +229,13 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
     ctx->device = device;
     ctx->cfg = *cfg;
     ctx->err[0] = 0;
+    if (const char *e = getenv("SSFE_MT_GO")) ctx->mt_go_at_start = strcmp(e, "stat") != 0;   // "stat" = old schedule (A/B hook)
     if (const char *e = getenv("SSFE_HOST_CHUNK_SAMPLES")) {     // test hook: force many small sub-batches
         const long long v = atoll(e);
-        if (v > 0) ctx->host_chunk_samples = v;
+        if (v > 0) {
+            ctx->host_chunk_samples = v;
+            ctx->host_chunk_forced = true;
+        }
     }
     ctx->mel_basis.assign(cfg->mel_basis, cfg->mel_basis + kBins * kMels);
     ctx->cfg.mel_basis = ctx->mel_basis.data();
@@ -431,6 +446,11 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     // validation paths - sequential filter mode, or a caller asking for the fp64 wav - keep the raw word
     // pairs and convert in the consumer, bit for bit numpy's doubles.
     const bool dith_f32 = ctx->cfg.filtfilt_mode != 1 && !o->wav64;
+    // Where the side stream may start.  The generator is ~3 G warp instructions of integer work.  Beside the
+    // previous call's stationarity kernel (the round-1 schedule, needed then because one warp walked a 4096-block
+    // segment for 5.5 ms) it took issue slots from a kernel that is issue bound: rapt_stat 13.5 -> 18.9 ms.  The
+    // filter passes it now runs beside are latency bound at ~30 % issue utilisation and absorb it.
+    if (ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, ctx->stream));
     mark(ctx, ST_RAND);
     if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux, dith_f32))) return rc;
     mark(ctx, ST_FILTFILT);
@@ -510,7 +530,12 @@ static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     // Sub-batches of ~kChunkSamples, cut preferably where the speaker changes.  The first upload and the
     // last download are not hidden behind anything, so the schedule ramps up (1/4, 1/2, 1, 1, ...) and
     // down again (..., 1/2, 1/4).
-    const int64_t kChunkSamples = ctx->host_chunk_samples;
+    // full-size sub-batch: an eighth of the call, between 16 M and 256 M samples.  (A constant 256 M cut the
+    // 262 M-sample share of one GPU of eight into 32 / 32 / 134 / 64 M - no pipeline to speak of.)  The test hook
+    // SSFE_HOST_CHUNK_SAMPLES overrides it.
+    const int64_t total_samples = b->sample_offsets[n] - b->sample_offsets[0];
+    const int64_t kChunkSamples = ctx->host_chunk_forced ? ctx->host_chunk_samples
+                                                         : std::min<int64_t>(std::max<int64_t>(total_samples / 8, 16LL << 20), 256LL << 20);
     std::vector<int64_t> targets;
     {
         // ramp up (T/8, T/8, T/4, T/4, T/2, T/2), full sub-batches, ramp down (T/2, T/4); a remainder too

@@ -56,7 +56,8 @@ struct ssfe_ctx {
     static constexpr int kHostLanes = 2;                      // compute lanes of ssfe_extract_host
     ssfe_ctx *lane[kHostLanes] = {};                          // (full contexts, created on first use)
     cudaEvent_t ev_dith_free = nullptr;                       // recorded after the kernel that reads `dith`
-    cudaEvent_t ev_mt_go = nullptr;                           // recorded where the NEXT call's dither walk may start
+    cudaEvent_t ev_mt_go = nullptr;                           // recorded where the dither walk may start
+    bool mt_go_at_start = true;                               // ... at the start of its own call (api.cu), not beside the previous call's rapt_stat
     char *aux_host[2] = {nullptr, nullptr}, *aux_dev[2] = {nullptr, nullptr};   // side-stream metadata staging
     size_t aux_cap[2] = {0, 0};
     cudaEvent_t aux_free[2] = {nullptr, nullptr};
@@ -75,6 +76,7 @@ struct ssfe_ctx {
     char *meta_host = nullptr;
     char *meta_dev = nullptr;
     size_t meta_cap = 0, meta_used = 0;
+    size_t meta_pend_off = 0, meta_pend_bytes = 0;            // staged in the pinned arena, not yet copied (flush_meta)
     std::vector<char *> retired_host, retired_dev;            // outgrown arenas, kept alive until destroy
     // tables
     float *d_window = nullptr;         // periodic Hann(1024)
@@ -94,7 +96,8 @@ struct ssfe_ctx {
     void *pin_in = nullptr;  size_t pin_in_cap = 0;
     void *pin_out = nullptr; size_t pin_out_cap = 0;
     ssfe::DevBuf h_x, h_mel, h_f0, h_bins;
-    long long host_chunk_samples = 256LL << 20;               // sub-batch size of ssfe_extract_host
+    long long host_chunk_samples = 256LL << 20;               // sub-batch size of ssfe_extract_host when forced (test hook)
+    bool host_chunk_forced = false;
 };
 
 namespace ssfe {
@@ -107,8 +110,11 @@ void mark(ssfe_ctx *ctx, int boundary);     // records event `boundary` (0..ST_C
 void mark_aux(ssfe_ctx *ctx, int which, cudaStream_t st);   // side-stream start (0) / end (1) of the current call
 int cuda_fail(ssfe_ctx *ctx, cudaError_t e, const char *what);
 int ensure(ssfe_ctx *ctx, DevBuf &b, size_t bytes);
-// copies `bytes` of host metadata to the device through the pinned arena; returns device pointer
+// stages `bytes` of host metadata in the pinned arena and returns the device pointer they will have; the copy
+// itself happens in flush_meta(), ONE copy kernel for everything staged since the last flush - a stage function
+// uploads all its arrays, flushes once, then launches (SSFE_LAUNCHED refuses a launch with staged data pending)
 void *upload_meta(ssfe_ctx *ctx, const void *host, size_t bytes);
+int flush_meta(ssfe_ctx *ctx);
 // pinned host -> device by a small kernel on `st` (keeps metadata off the copy engines, see api.cu)
 int stage_copy(ssfe_ctx *ctx, void *dst_dev, const void *src_pinned, size_t bytes, cudaStream_t st);
 template <typename T>
@@ -126,6 +132,8 @@ inline T *upload(ssfe_ctx *ctx, const T *host, size_t n)
 #define SSFE_LAUNCHED(ctx)                                              \
     do {                                                                \
         (ctx)->launches++;                                              \
+        if ((ctx)->meta_pend_bytes)                                     \
+            return ::ssfe::set_error(ctx, SSFE_ERR_INVALID, "internal error: kernel launched with unflushed metadata (%s:%d)", __FILE__, __LINE__); \
         cudaError_t e__ = cudaGetLastError();                           \
         if (e__ != cudaSuccess) return ::ssfe::cuda_fail(ctx, e__, "kernel launch"); \
     } while (0)

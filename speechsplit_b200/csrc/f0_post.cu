@@ -237,6 +237,7 @@ int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_hos
         reinterpret_cast<char *>(ctx->ws.misc.p) + (total * sizeof(float) + static_cast<size_t>(n) * 2 * sizeof(float) + 7) / 8 * 8);
     int64_t *d_off = upload(ctx, frame_off_host, n + 1);
     if (!d_off) return SSFE_ERR_NOMEM;
+    if ((rc = flush_meta(ctx))) return rc;
     f0_stats_kernel<<<static_cast<unsigned>(grid_for(n, 64)), 64, 0, ctx->stream>>>(f0_dev, d_off, n, scratch, stats);
     SSFE_LAUNCHED(ctx);
     int64_t *use_bins = bins ? bins : (onehot ? tmp_bins : nullptr);
@@ -371,6 +372,7 @@ extern "C" int ssfe_collate(ssfe_ctx *ctx, const float *mel_dev, const float *f0
     int *d_utt = upload(ctx, utt, n_items), *d_left = upload(ctx, left, n_items),
         *d_len = upload(ctx, len_crop, n_items);
     if (!d_off || !d_utt || !d_left || !d_len) return SSFE_ERR_NOMEM;
+    if (int rcf = flush_meta(ctx)) return rcf;
     dim3 grid(max_len_pad, n_items);
     collate_kernel<<<grid, 96, 0, ctx->stream>>>(mel_dev, f0_norm_dev, d_off, d_utt, d_left, d_len, max_len_pad,
                                                  melsp_dev, pitch_dev, onehot_dev, bins_dev);

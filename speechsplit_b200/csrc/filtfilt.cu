@@ -731,6 +731,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.chunk_off = upload(ctx, chunk_off.data(), n + 1);
     const int *d_tile_off = upload(ctx, tile_off.data(), n + 1);
     if (!p.in_off || !p.fix_off || !p.chunk_off || !d_tile_off) return SSFE_ERR_NOMEM;
+    if (int rcf = flush_meta(ctx)) return rcf;
     const int n_tiles = static_cast<int>(tiles);
     {
         const int rc_map = ensure(ctx, ctx->ws.filt_map, (tiles + 1) * sizeof(int));

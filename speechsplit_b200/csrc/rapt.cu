@@ -230,6 +230,7 @@ __device__ __forceinline__ float warp_max(float v)
 // peaks of correl[0..nl) above cand_thresh*maxval, in ascending lag order (get_cand)
 // [i_lo, i_hi): the index range that can hold non-zero correlations (everything outside is zero and,
 // with clip >= 0, can never be a peak), so the scan may skip it
+template <int CAP>
 __device__ __forceinline__ int pick_candidates(const float *cc, int nl, int firstlag, float maxval,
                                                float *peaks, int *locs, int lane, int i_lo = 1, int i_hi = 1 << 30)
 {
@@ -246,14 +247,14 @@ __device__ __forceinline__ int pick_candidates(const float *cc, int nl, int firs
         }
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         const int pos = count + __popc(mask & ((1u << lane) - 1u));
-        if (ok && pos < kPkMax) {
+        if (ok && pos < CAP) {
             peaks[pos] = q;
             locs[pos] = i + firstlag;
         }
         count += __popc(mask);
     }
     __syncwarp();
-    return min(count, kPkMax);
+    return min(count, CAP);
 }
 
 // keep the n_cands-1 largest, by the original's partial bubble pass (order matters downstream)
@@ -280,27 +281,42 @@ __device__ __forceinline__ int prune_candidates(float *peaks, int *locs, int nca
 }
 
 // ---- K2 ------------------------------------------------------------------------------------
+// A CTA takes 16 consecutive frames of one utterance, a warp four of them (frames w, w + 4, w + 8, w + 12 of
+// the tile).  Everything that is a long sequential chain - and RAPT's fine stage is nothing else: per frame a
+// 120-term mean, a 120-term reference energy, and per coarse candidate a 120-term window energy plus SEVEN
+// 120-term cross products - is advanced for the warp's four frames TOGETHER, one lane per (frame, candidate):
+//   * the lane keeps the candidate's 7-lag window  x[st + j .. st + j + 6]  as a sliding window in registers:
+//     one new shared-memory value per step feeds all seven cross products and the window energy (the first
+//     version read one value per multiply, and ncu had the kernel at 91 % of the shared-memory pipe);
+//   * the reference sample ref[j] arrives as a 128-bit read shared by the lanes of a frame;
+//   * every chain is still one left-to-right sum by one thread, product rounded before the add (--fmad=false),
+//     so the bits are those of the serial original;
+//   * the reference energy of a frame is one more item (a pseudo-candidate at lag 0 whose cross products are
+//     ignored), so it costs no pass of its own.
+// With ~3 coarse candidates per frame a warp's four frames are ~16 items, i.e. one pass of 120 steps; a group of
+// frames whose items exceed 32 is split (warp-uniformly) into several passes.
+// Shared memory per warp: four mean-free 441-sample windows at a stride of 456 floats (the four frames start
+// 8 banks apart, so the per-frame broadcast reads of one instruction never collide).  The coarse stage's scratch
+// and, later, the per-frame correlation array and peak lists alias the window of frame 0 (dead by then).
 constexpr int kCandWarps = 4;
+constexpr int kCandTile = 16;      // frames per CTA (4 per warp)
+constexpr int kXfStride = 456;     // >= ncomp (441), = 8 mod 32, multiple of 4
+constexpr int kFinePk = 84;        // peaks of the fine correlation: it is non-zero on <= 20 x 7 lags, so <= 70
 
-constexpr int kCandTile = 16;      // frames per CTA (one binary search per tile, 4 frames per warp)
-
-__global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off,
+__global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off,
                                                                     const int *__restrict__ tile_map)
 {
-    __shared__ __align__(16) float s_db[kCandWarps][448];
-    __shared__ __align__(16) float s_cc[kCandWarps][kCcMax];        // fine stage: first the lagged energies (double[140])
-    __shared__ float s_val[kCandWarps][kCMax * 7 + 4];
-    __shared__ __align__(16) float s_pklc[kCandWarps][2 * kPkMax];  // peaks | lags; between prune and pick: fine squares
-    __shared__ int s_st[kCandWarps][kCMax];
-
+    __shared__ __align__(16) float s_xf[kCandWarps][4 * kXfStride];
     // candidates of the warp's four frames after the coarse stage: [4][20] peaks, [4][20] lags, [4] counts
     __shared__ __align__(16) float s_stash[kCandWarps][4 * kCMax + 4 * kCMax + 4];
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float *db = s_db[w], *cc = s_cc[w], *val = s_val[w], *pk = s_pklc[w];
-    int *lc = reinterpret_cast<int *>(s_pklc[w] + kPkMax), *stc = s_st[w];
-    float *sqf = s_pklc[w];                        // [448] squares of the mean-free fine window
-    double *ecf = reinterpret_cast<double *>(s_cc[w]);   // [7 * ncand] lagged energy of every (candidate, lag)
+    float *xf = s_xf[w];
+    // aliases inside the window of frame 0 (per-frame phase) ...
+    float *cc = xf;                                                   // [kCcMax = 288] fine correlation
+    float *pk = xf + kCcMax;                                          // [kFinePk] peaks
+    int *lc = reinterpret_cast<int *>(xf + kCcMax + kFinePk);         // [kFinePk] lags
+    static_assert(kCcMax + 2 * kFinePk <= kXfStride, "per-frame buffers must fit the window of frame 0");
 
     const int u = tile_map[blockIdx.x];
     const RaptUtt ut = p.utts[u];
@@ -316,7 +332,7 @@ __global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const Rap
     // update) that one lane has to walk: with a whole warp per frame they ran on 1 lane of 32, here four
     // frames' chains advance together.  Control flow is uniform across the warp (same configuration for
     // all frames of an utterance), validity is a predicate, so every __syncwarp / ballot is convergent.
-    // The working buffers alias the fine-stage arrays, which are idle until the loop below.
+    // The working buffers alias the fine-stage windows, which are idle until the staging below.
     {
         const int sub = lane >> 3, l8 = lane & 7;
         const int gq = g_tile + w + kCandWarps * sub;
@@ -324,11 +340,12 @@ __global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const Rap
         // (strides of 72 floats / 44 doubles, not 64 / 40: the four quarter-warps then start 8 banks apart
         // instead of on the same bank - the plain layout made every access of this stage a 4-way conflict,
         // a quarter of the kernel's shared-memory wavefronts in ncu)
-        float *cdb = s_cc[w] + 72 * sub;                           // [64] coarse window
-        double *cec = reinterpret_cast<double *>(s_db[w]) + 44 * sub;   // [40] lagged energy per lag
-        float *ccc = s_pklc[w] + 40 * sub;                         // [40] coarse correlation
-        float *cpk = s_pklc[w] + 160 + kCMax * sub;                // [20] peaks
-        int *clc = reinterpret_cast<int *>(s_pklc[w] + 160 + 4 * kCMax) + kCMax * sub;   // [20] lags
+        float *cdb = xf + 72 * sub;                                // [64] coarse window
+        double *cec = reinterpret_cast<double *>(xf + 288) + 44 * sub;   // [40] lagged energy per lag
+        float *ccc = xf + 288 + 352 + 40 * sub;                    // [40] coarse correlation
+        float *cpk = xf + 288 + 352 + 160 + kCMax * sub;           // [20] peaks
+        int *clc = reinterpret_cast<int *>(xf + 288 + 352 + 160 + 4 * kCMax) + kCMax * sub;   // [20] lags
+        static_assert(288 + 352 + 160 + 8 * kCMax <= 4 * kXfStride, "coarse scratch must fit the window buffers");
         int r, i, nfr_r;
         const int full = ut.R_last * cf.F;
         if (gc < full) { r = gc / cf.F; i = gc - r * cf.F; nfr_r = cf.F; }
@@ -469,187 +486,199 @@ __global__ void __launch_bounds__(kCandWarps * 32, 8) rapt_cand_kernel(const Rap
             st_pk[kCMax * sub + c] = cpk[c];
             st_lc[kCMax * sub + c] = clc[c];
         }
-        if (l8 == 0) st_n[sub] = ncand_c;
+        if (l8 == 0) st_n[sub] = (gq < ut.n_fr) ? ncand_c : -1;      // -1: no such frame
         __syncwarp();
     }
 
-  for (int fq = 0; fq < kCandTile / kCandWarps; ++fq) {
-    const int g = g_tile + w + kCandWarps * fq;
-    if (g >= ut.n_fr) break;
-    const long long gf = ut.fr_off + g;
-    float maxval = 0.0f;
-    int ncand = st_n[fq];
-    if (lane < ncand) {
-        pk[lane] = st_pk[kCMax * fq + lane];
-        lc[lane] = st_lc[kCMax * fq + lane];
+    // -- fine stage: stage the four windows, mean-free ------------------------------------------------
+    const int start0 = cf.start, nlags0 = cf.nlags, total = cf.ncomp;   // size + nlags0 + start0
+    int nfq = 0;                                                   // frames of this warp that exist (a prefix)
+#pragma unroll
+    for (int f = 0; f < 4; ++f) nfq += (g_tile + w + kCandWarps * f < ut.n_fr) ? 1 : 0;
+    if (nfq == 0) return;
+    for (int f = 0; f < nfq; ++f) {
+        const float *fx = x + static_cast<long long>(g_tile + w + kCandWarps * f) * kHop;
+        float raw[14];
+#pragma unroll
+        for (int q = 0; q < 14; ++q) raw[q] = fx[min(lane + 32 * q, total - 1)];
+#pragma unroll
+        for (int q = 0; q < 14; ++q)
+            if (lane + 32 * q < total) xf[f * kXfStride + lane + 32 * q] = raw[q] * 32768.0f;
     }
     __syncwarp();
-
-    // -- fine stage on the full-rate signal ---------------------------------------------------------
     {
-        const int start0 = cf.start, nlags0 = cf.nlags, total = cf.ncomp;   // size + nlags0 + start0
-        const float *fx = x + static_cast<long long>(g) * kHop;
-        {
-            float raw[14];
-#pragma unroll
-            for (int q = 0; q < 14; ++q) raw[q] = fx[min(lane + 32 * q, total - 1)];
-#pragma unroll
-            for (int q = 0; q < 14; ++q)
-                if (lane + 32 * q < total) db[lane + 32 * q] = raw[q] * 32768.0f;
-        }
-        __syncwarp();
-        // mean of the reference window: one left-to-right chain, computed by every lane from
-        // broadcast 128-bit reads
-        float engr = 0.0f;
+        // mean of the reference window: one left-to-right chain per frame, lane f walks frame f
+        float mean = 0.0f;
+        if (lane < nfq) {
+            const float *q = xf + lane * kXfStride;
 #pragma unroll 6
-        for (int j = 0; j < kWin; j += 4) {
-            const float4 v4 = *reinterpret_cast<const float4 *>(db + j);
-            engr += v4.x;
-            engr += v4.y;
-            engr += v4.z;
-            engr += v4.w;
-        }
-        engr /= kWin;
-        // first lag of every candidate's 7-lag window (the lists themselves are not needed again
-        // before pick_candidates rewrites them, so their storage holds the squares below)
-        int my_st = 0;
-        if (lane < ncand) {
-            my_st = lc[lane] - 3;
-            if (my_st < start0) my_st = start0;
-            stc[lane] = my_st;
-        }
-        __syncwarp();
-        for (int t = lane; t < total; t += 32) {
-            const float v = db[t] - engr;
-            db[t] = v;
-            sqf[t] = v * v;
-        }
-        __syncwarp();
-        // window energies in ONE pass: lanes < ncand sum their candidate's first lagged window, lane 31
-        // sums the reference window (each still a single left-to-right float chain)
-        float s2 = 0.0f;
-        if (lane < ncand || lane == 31) {
-            const float *q = sqf + my_st;
-#pragma unroll 20
-            for (int j = 0; j < kWin; ++j) s2 += q[j];
-        }
-        engr = __shfl_sync(0xffffffffu, s2, 31);
-        maxval = 0.0f;
-        // The fine correlation is non-zero only inside the 7-lag windows, so only the span of those
-        // windows (plus one zero on either side, which the peak test reads) is cleared and scanned.
-        int z_lo = 0, z_hi = 0;
-        {
-            int mn = (lane < ncand) ? my_st : (1 << 30), mx = (lane < ncand) ? my_st : -(1 << 30);
-            mn = __reduce_min_sync(0xffffffffu, mn);
-            mx = __reduce_max_sync(0xffffffffu, mx);
-            if (ncand > 0) {
-                z_lo = max(mn - start0 - 1, 0);
-                z_hi = min(mx - start0 + 7 + 1, nlags0);
+            for (int j = 0; j < kWin; j += 4) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(q + j);
+                mean += v4.x;
+                mean += v4.y;
+                mean += v4.z;
+                mean += v4.w;
             }
+            mean /= kWin;
         }
-        if (engr > 0.0f) {
-            float vmax = 0.0f;
-            // cross products, one left-to-right chain per (candidate, lag).  With more than 32 chains a
-            // lane takes two at once: the reference samples are read once (broadcast float4) and the
-            // two chains advance together as one packed multiply + add.
-            const int nwk = ncand * 7;
-            for (int wk0 = 0; wk0 < nwk; wk0 += 64) {
-                const int wa = wk0 + lane, wb = wa + 32;
-                const int ca = min(wa, nwk - 1) / 7, ta = min(wa, nwk - 1) - 7 * ca;
-                const float *pa = db + stc[ca] + ta;
-                if (wk0 + 32 < nwk) {
-                    const int cb = min(wb, nwk - 1) / 7, tb = min(wb, nwk - 1) - 7 * cb;
-                    const float *pb = db + stc[cb] + tb;
-                    p2 dot = p2pack(0.0f, 0.0f);
-#pragma unroll 2
-                    for (int j = 0; j < kWin; j += 4) {
-                        const float4 r4 = *reinterpret_cast<const float4 *>(db + j);
-                        dot = p2add(dot, p2mul(p2pack(r4.x, r4.x), p2pack(pa[j], pb[j])));
-                        dot = p2add(dot, p2mul(p2pack(r4.y, r4.y), p2pack(pa[j + 1], pb[j + 1])));
-                        dot = p2add(dot, p2mul(p2pack(r4.z, r4.z), p2pack(pa[j + 2], pb[j + 2])));
-                        dot = p2add(dot, p2mul(p2pack(r4.w, r4.w), p2pack(pa[j + 3], pb[j + 3])));
-                    }
-                    if (wa < nwk) val[wa] = p2lo(dot);
-                    if (wb < nwk) val[wb] = p2hi(dot);
-                } else {
-                    float dot = 0.0f;
-#pragma unroll 2
-                    for (int j = 0; j < kWin; j += 4) {
-                        const float4 r4 = *reinterpret_cast<const float4 *>(db + j);
-                        dot += r4.x * pa[j];
-                        dot += r4.y * pa[j + 1];
-                        dot += r4.z * pa[j + 2];
-                        dot += r4.w * pa[j + 3];
-                    }
-                    if (wa < nwk) val[wa] = dot;
-                }
-            }
-            // lagged energies: a short sequential double chain per candidate ...
-            if (lane < ncand) {
-                const float *q = sqf + my_st;
-                double engc = s2;
-#pragma unroll
-                for (int t = 0; t < 7; ++t) {
-                    if (engc < 1.0) engc = 1.0;
-                    ecf[lane * 7 + t] = engc;
-                    engc -= static_cast<double>(q[t]);
-                    engc += static_cast<double>(q[t + kWin]);
-                }
-            }
-            __syncwarp();
-            // ... and the expensive part (double square root and division) spread over all lanes
-            for (int wk = lane; wk < nwk; wk += 32) {
-                const float v = static_cast<float>(val[wk] / sqrt(10000.0 + (ecf[wk] * engr)));
-                val[wk] = v;
-                vmax = fmaxf(vmax, v);
-            }
-            __syncwarp();
-            for (int t = z_lo + lane; t < z_hi; t += 32) cc[t] = 0.0f;      // (the energies lived here)
-            __syncwarp();
-            // windows are written in candidate order; later ones overwrite earlier ones
-            for (int c = 0; c < ncand; ++c) {
-                const int o = stc[c] - start0 + lane;
-                if (lane < 7 && o < kCcMax) cc[o] = val[c * 7 + lane];
-                __syncwarp();
-            }
-            maxval = warp_max(vmax);       // max over every value computed (order independent)
+        for (int f = 0; f < nfq; ++f) {
+            const float m = __shfl_sync(0xffffffffu, mean, f);
+            float *q = xf + f * kXfStride;
+            for (int t = lane; t < total; t += 32) q[t] = q[t] - m;
         }
-        __syncwarp();
-        ncand = (engr > 0.0f) ? pick_candidates(cc, nlags0, start0, maxval, pk, lc, lane, z_lo + 1, z_hi - 1) : 0;
-        ncand = prune_candidates(pk, lc, ncand, lane);
-
-        // local costs (A5) and the value each candidate would emit (A8)
-        const float lagwt = cf.lagwt;
-        short *oloc = p.loc + gf * kCMax;
-        float *omp = p.mp + gf * kCMax, *of0 = p.f0c + gf * kCMax;
-        if (lane < ncand) {
-            const int loc1 = lc[lane];
-            const float pv = pk[lane];
-            float ftemp = 1.0 - (static_cast<float>(loc1) * lagwt);
-            omp[lane] = 1.0 - (pv * ftemp);
-            oloc[lane] = static_cast<short>(loc1);
-            ftemp = loc1;
-            if (loc1 > cf.start && loc1 < cf.stop) {
-                const int jj = loc1 - cf.start;
-                const float cormax = cc[jj], cprev = cc[jj + 1], cnext = cc[jj - 1];
-                const float den = (2.0 * (cprev + cnext - (2.0 * cormax)));
-                if (fabs(den) > 0.000001)
-                    ftemp += 2.0 - ((((5.0 * cprev) + (3.0 * cnext) - (8.0 * cormax)) / den));
-            }
-            of0[lane] = 16000.0 / ftemp;
-        } else if (lane == ncand) {
-            oloc[lane] = -1;
-            omp[lane] = c_rapt.vbias + maxval;
-            of0[lane] = 0.0f;
-        } else if (lane < kCMax) {
-            oloc[lane] = -1;
-            omp[lane] = 0.0f;
-            of0[lane] = 0.0f;
-        }
-        if (lane == 0) p.ncand[gf] = static_cast<unsigned char>(ncand + 1);
     }
     __syncwarp();
-  }   // frames of this warp
+
+    // -- groups of frames whose items (candidates + one reference item per frame) fit the 32 lanes -------
+    for (int f_begin = 0; f_begin < nfq;) {
+        int f_end = f_begin, n_items = 0;
+        while (f_end < nfq && n_items + st_n[f_end] + 1 <= 32) {
+            n_items += st_n[f_end] + 1;
+            ++f_end;
+        }
+        // this lane's item: frame my_f, candidate my_c (== count of the frame: the reference item)
+        int my_f = f_begin, my_c = lane, base_f = 0;
+        while (my_f < f_end && my_c > st_n[my_f]) {
+            my_c -= st_n[my_f] + 1;
+            base_f += st_n[my_f] + 1;
+            ++my_f;
+        }
+        const bool active = my_f < f_end;
+        if (!active) { my_f = f_begin; my_c = st_n[f_begin]; base_f = 0; }   // idle lanes shadow a reference item
+        const bool is_ref = my_c == st_n[my_f];
+        int my_st = 0;
+        if (!is_ref) {
+            my_st = st_lc[kCMax * my_f + my_c] - 3;
+            if (my_st < start0) my_st = start0;
+        }
+        const float *xr = xf + my_f * kXfStride;       // reference window of my frame
+        const float *xs = xr + my_st;                  // my candidate's first lagged window
+        float wv[7], dot[7], s2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { wv[k] = xs[k]; dot[k] = 0.0f; }
+        // 120 steps; at step j the registers hold x[st + j .. st + j + 6] (wv[(j + t) % 7] = x[st + j + t])
+#pragma unroll 1
+        for (int jb = 0; jb < 112; jb += 28) {
+#pragma unroll
+            for (int jj = 0; jj < 28; jj += 4) {
+                const float4 r4 = *reinterpret_cast<const float4 *>(xr + jb + jj);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float r = (q == 0) ? r4.x : (q == 1) ? r4.y : (q == 2) ? r4.z : r4.w;
+                    const int ph = (jj + q) % 7;
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) dot[t] += r * wv[(ph + t) % 7];
+                    s2 += wv[ph] * wv[ph];
+                    wv[ph] = xs[jb + jj + q + 7];
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; jj += 4) {             // steps 112 .. 119 (112 = 0 mod 7)
+            const float4 r4 = *reinterpret_cast<const float4 *>(xr + 112 + jj);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = (q == 0) ? r4.x : (q == 1) ? r4.y : (q == 2) ? r4.z : r4.w;
+                const int ph = (jj + q) % 7;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) dot[t] += r * wv[(ph + t) % 7];
+                s2 += wv[ph] * wv[ph];
+                wv[ph] = xs[112 + jj + q + 7];
+            }
+        }
+        // reference energy of my frame: from the lane that holds its reference item
+        const float engr = __shfl_sync(0xffffffffu, s2, base_f + st_n[my_f]);
+        float vmax = 0.0f;
+        if (engr > 0.0f && !is_ref) {
+            // lagged energies: a short sequential double chain, then square root and division
+            double engc = s2;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                if (engc < 1.0) engc = 1.0;
+                const float v = static_cast<float>(dot[t] / sqrt(10000.0 + (engc * engr)));
+                dot[t] = v;
+                vmax = fmaxf(vmax, v);
+                const float a0 = xs[t], az = xs[t + kWin];
+                engc -= static_cast<double>(a0 * a0);
+                engc += static_cast<double>(az * az);
+            }
+        }
+        __syncwarp();          // every lane is done with the windows of this group (frame 0's is overwritten below)
+
+        // -- per frame: correlation array, peaks, pruning, local costs --------------------------------------
+        int fbase = 0;
+        for (int f = f_begin; f < f_end; ++f) {
+            const int ncand_c = st_n[f];
+            const int g = g_tile + w + kCandWarps * f;
+            const long long gf = ut.fr_off + g;
+            const bool mine = active && my_f == f && !is_ref;
+            const float engr_f = __shfl_sync(0xffffffffu, s2, fbase + ncand_c);
+            // The fine correlation is non-zero only inside the 7-lag windows, so only the span of those
+            // windows (plus one zero on either side, which the peak test reads) is cleared and scanned.
+            int z_lo = 0, z_hi = 0;
+            {
+                const int mn = __reduce_min_sync(0xffffffffu, mine ? my_st : (1 << 30));
+                const int mx = __reduce_max_sync(0xffffffffu, mine ? my_st : -(1 << 30));
+                if (ncand_c > 0) {
+                    z_lo = max(mn - start0 - 1, 0);
+                    z_hi = min(mx - start0 + 7 + 1, nlags0);
+                }
+            }
+            float maxval = 0.0f;
+            int ncand = 0;
+            if (engr_f > 0.0f) {
+                for (int t = z_lo + lane; t < z_hi; t += 32) cc[t] = 0.0f;
+                __syncwarp();
+                // windows are written in candidate order; later ones overwrite earlier ones
+                for (int c = 0; c < ncand_c; ++c) {
+                    if (mine && my_c == c) {
+                        const int o = my_st - start0;
+#pragma unroll
+                        for (int t = 0; t < 7; ++t)
+                            if (o + t < kCcMax) cc[o + t] = dot[t];
+                    }
+                    __syncwarp();
+                }
+                // max over every value computed (order independent; all values are >= 0 after the fmaxf with 0)
+                maxval = __uint_as_float(__reduce_max_sync(0xffffffffu, mine ? __float_as_uint(vmax) : 0u));
+                ncand = pick_candidates<kFinePk>(cc, nlags0, start0, maxval, pk, lc, lane, z_lo + 1, z_hi - 1);
+            }
+            ncand = prune_candidates(pk, lc, ncand, lane);
+
+            // local costs (A5) and the value each candidate would emit (A8)
+            const float lagwt = cf.lagwt;
+            short *oloc = p.loc + gf * kCMax;
+            float *omp = p.mp + gf * kCMax, *of0 = p.f0c + gf * kCMax;
+            if (lane < ncand) {
+                const int loc1 = lc[lane];
+                const float pv = pk[lane];
+                float ftemp = 1.0 - (static_cast<float>(loc1) * lagwt);
+                omp[lane] = 1.0 - (pv * ftemp);
+                oloc[lane] = static_cast<short>(loc1);
+                ftemp = loc1;
+                if (loc1 > cf.start && loc1 < cf.stop) {
+                    const int jj = loc1 - cf.start;
+                    const float cormax = cc[jj], cprev = cc[jj + 1], cnext = cc[jj - 1];
+                    const float den = (2.0 * (cprev + cnext - (2.0 * cormax)));
+                    if (fabs(den) > 0.000001)
+                        ftemp += 2.0 - ((((5.0 * cprev) + (3.0 * cnext) - (8.0 * cormax)) / den));
+                }
+                of0[lane] = 16000.0 / ftemp;
+            } else if (lane == ncand) {
+                oloc[lane] = -1;
+                omp[lane] = c_rapt.vbias + maxval;
+                of0[lane] = 0.0f;
+            } else if (lane < kCMax) {
+                oloc[lane] = -1;
+                omp[lane] = 0.0f;
+                of0[lane] = 0.0f;
+            }
+            if (lane == 0) p.ncand[gf] = static_cast<unsigned char>(ncand + 1);
+            __syncwarp();
+            fbase += ncand_c + 1;
+        }
+        f_begin = f_end;
+    }
 }
 
 // ---- K3 ------------------------------------------------------------------------------------
@@ -1046,6 +1075,24 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
         for (int t = lane; t < ut.n_fr; t += 32) out[t] = kUnvoiced;
 }
 
+// tile -> utterance lookups of the three frame-parallel kernels in one launch (blockIdx.y picks the table)
+__global__ void rapt_maps_kernel(const long long *__restrict__ ds_offs, const int *__restrict__ cand_tiles,
+                                 const int *__restrict__ stat_tiles, int n, int *__restrict__ dec_map,
+                                 int *__restrict__ cand_map, int *__restrict__ stat_map)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    if (blockIdx.y == 0) {
+        const long long t1 = ds_offs[u + 1] / kDecTile;
+        for (long long t = ds_offs[u] / kDecTile; t < t1; ++t) dec_map[t] = u;
+    } else {
+        const int *off = (blockIdx.y == 1) ? cand_tiles : stat_tiles;
+        int *map = (blockIdx.y == 1) ? cand_map : stat_map;
+        const int t1 = off[u + 1];
+        for (int t = off[u]; t < t1; ++t) map[t] = u;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 static int iround(double x) { return static_cast<int>(x + 0.5); }
 
@@ -1258,6 +1305,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     p.fr_offs = upload(ctx, fr_offs.data(), n + 1);
     p.ds_offs = upload(ctx, ds_offs.data(), n + 1);
     if (!p.utts || !p.fr_offs || !p.ds_offs) return SSFE_ERR_NOMEM;
+    if ((rc = flush_meta(ctx))) return rc;
     p.n = n;
     p.total_fr = fr;
     p.total_ds = dsn;
@@ -1287,11 +1335,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     T->last_rr = p.rr;
 
     cudaStream_t st = ctx->stream;
-    segment_map_kernel<long long><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p.ds_offs, n, kDecTile, dec_map);
-    SSFE_LAUNCHED(ctx);
-    segment_map_kernel<int><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_cand_tiles, n, 1, cand_map);
-    SSFE_LAUNCHED(ctx);
-    segment_map_kernel<int><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_stat_tiles, n, 1, stat_map);
+    rapt_maps_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), 3), 256, 0, st>>>(p.ds_offs, d_cand_tiles, d_stat_tiles, n, dec_map,
+                                                                                       cand_map, stat_map);
     SSFE_LAUNCHED(ctx);
     rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecThreads, 0, st>>>(p, dec_map);
     SSFE_LAUNCHED(ctx);
@@ -1300,16 +1345,14 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles, cand_map);
         SSFE_LAUNCHED(ctx);
         mark(ctx, ST_RAPT_STAT);
-        // The next call's dither generation (side stream, high priority) may start here: the stationarity
-        // kernel holds only 10 warps per SM, the Viterbi kernel and the F0 post-processing are latency /
-        // write bound, so its ~5 ms of work fit beside them - and at 1/8 of the corpus (one GPU of
-        // eight) its 1.5 ms segment walks need the head start to be done before the backward filter pass.
-        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
+        // (mt_go_at_start == false, the earlier schedule:) the next call's dither generation (side stream, high
+        // priority) may start here, beside the stationarity kernel - see extract_device for why it no longer does.
+        if (!ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
         rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles, stat_map);
         SSFE_LAUNCHED(ctx);
     } else {
         mark(ctx, ST_RAPT_STAT);
-        SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
+        if (!ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
     }
     mark(ctx, ST_RAPT_DP);
     rapt_dp_kernel<<<static_cast<unsigned>((n + kDpWarps - 1) / kDpWarps), kDpWarps * 32, 0, st>>>(p);

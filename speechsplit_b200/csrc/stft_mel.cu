@@ -306,6 +306,7 @@ int pad_reflect(ssfe_ctx *ctx, const float *wav_dev, const int64_t *offsets_host
     int64_t *d_off = upload(ctx, offsets_host, n + 1);
     int64_t *d_seg = upload(ctx, seg_off_host.data(), n + 1);
     if (!d_off || !d_seg) return SSFE_ERR_NOMEM;
+    if ((rc = flush_meta(ctx))) return rc;
     dim3 grid(static_cast<unsigned>(std::min<int64_t>((maxL + 1024 + 255) / 256, 64)),
               static_cast<unsigned>(std::min(n, 32768)));
     pad_reflect_kernel<<<grid, 256, 0, ctx->stream>>>(wav_dev, d_off, d_seg, n,
@@ -337,6 +338,7 @@ int stft_padded(ssfe_ctx *ctx, const float *wavp, const int64_t *seg_off_host, c
     const int *d_pair_off = upload(ctx, pair_off.data(), n + 1);
     const int64_t *d_frame_off = upload(ctx, frame_off.data(), n + 1);
     if (!d_seg || !d_pair_off || !d_frame_off) return SSFE_ERR_NOMEM;
+    if ((rc = flush_meta(ctx))) return rc;
     PairInfo *d_pairs = static_cast<PairInfo *>(ctx->ws.tiles.p);
     stft_pairs_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, ctx->stream>>>(
         d_seg, d_pair_off, d_frame_off, n, static_cast<int>(pairs), d_pairs);
