@@ -123,6 +123,17 @@ int ssfe_mt_charpoly_terms(int *exps, int cap);
 int ssfe_mt_jump_poly(uint64_t n_words, uint64_t *poly312);
 int ssfe_mt_jump_taps(uint64_t unit_words, int level, int d, uint16_t *taps, int cap);
 
+/* Host-only helper behind ssfe_filtfilt / ssfe_extract (no GPU needed; exported so that the algebra can be
+ * tested on the CPU against scipy).  scipy.signal.filtfilt (make_spect_f0.py:54) runs ONE order-5 DF2T recurrence
+ * over (b, a); the chunked scan evaluates the same transfer function, with the same initial condition zi * x[0],
+ * as a cascade of one first-order and two second-order sections (csrc/filt_consts.cpp, 113-bit algebra).
+ *   sec   [3][5]  b0, b1, b2, a1, a2 of the sections in evaluation order (section 0: b2 = a2 = 0)
+ *   zic   [5]     cascade state equivalent to scipy's lfilter_zi vector zi5
+ *   m     [25]    (cascade state matrix)^chunk, row-major
+ * Returns 0, or a negative code when (b6, a6) does not factor into stable real sections. */
+int ssfe_filt_cascade(const double *b6, const double *a6, const double *zi5, int chunk, double *sec, double *zic,
+                      double *m);
+
 /* (a3) utils.pySTFT(x) (utils.py:18-31) for 1-D inputs: reflect-pad 512, hop 256, periodic
  * Hann(1024), |rfft|.  wav_dev float32 concatenated, offsets host [n+1] (lengths as given, no
  * fix-up).  mag_dev: float32 [total_frames, 513] (frame-major, i.e. the transpose of pySTFT's

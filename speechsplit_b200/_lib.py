@@ -60,6 +60,7 @@ SIGNATURES = {
     "ssfe_rand": (ctypes.c_int, [vp, c_u32p, c_u64p, c_i64p, ctypes.c_int, vp]),
     "ssfe_interp_lnr": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, vp]),
+    "ssfe_filt_cascade": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
     "ssfe_mt_charpoly_terms": (ctypes.c_int, [vp, ctypes.c_int]),
     "ssfe_mt_jump_poly": (ctypes.c_int, [ctypes.c_uint64, vp]),
     "ssfe_mt_jump_taps": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int]),

@@ -229,7 +229,7 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
     ctx->device = device;
     ctx->cfg = *cfg;
     ctx->err[0] = 0;
-    if (const char *e = getenv("SSFE_MT_GO")) ctx->mt_go_at_start = strcmp(e, "stat") != 0;   // "stat" = old schedule (A/B hook)
+    if (const char *e = getenv("SSFE_MT_GO")) ctx->mt_go_at_start = strcmp(e, "start") == 0;   // "stat" = old schedule (A/B hook)
     if (const char *e = getenv("SSFE_HOST_CHUNK_SAMPLES")) {     // test hook: force many small sub-batches
         const long long v = atoll(e);
         if (v > 0) {
@@ -442,14 +442,16 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
 
     // the dither stream is independent of the signal until the very last filtfilt kernel: generate
     // it on a side stream while the forward / backward-local passes run
-    // Production path: the generator leaves the finished dither term as float (4 bytes per sample).  The
-    // validation paths - sequential filter mode, or a caller asking for the fp64 wav - keep the raw word
-    // pairs and convert in the consumer, bit for bit numpy's doubles.
+    // Production path: the generator leaves one raw word per sample (4 bytes; the float dither term is formed from
+    // its 27 random bits in the consumer, mt_convert.cuh).  The validation paths - sequential filter mode, or a
+    // caller asking for the fp64 wav - keep the raw word pairs and convert bit for bit to numpy's doubles.
     const bool dith_f32 = ctx->cfg.filtfilt_mode != 1 && !o->wav64;
-    // Where the side stream may start.  The generator is ~3 G warp instructions of integer work.  Beside the
-    // previous call's stationarity kernel (the round-1 schedule, needed then because one warp walked a 4096-block
-    // segment for 5.5 ms) it took issue slots from a kernel that is issue bound: rapt_stat 13.5 -> 18.9 ms.  The
-    // filter passes it now runs beside are latency bound at ~30 % issue utilisation and absorb it.
+    // Where the side stream may start: by default beside the PREVIOUS call's stationarity kernel (rapt_run records
+    // ev_mt_go there), i.e. as early as the dither buffer is free.  For a large batch it makes no difference where
+    // the generator's ~2 G warp instructions run - measured on the full corpus: rapt_stat 18.9 + filtfilt 17.8 ms
+    // against 13.4 + 23.3 ms when it waits for its own call to start, the same total - but for a small batch (one
+    // GPU's share of eight) its 2.9 ms jump + walk latency chain is longer than the forward filter passes it could
+    // hide behind, and the head start covers it.  SSFE_MT_GO=start forces the late start (A/B hook).
     if (ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, ctx->stream));
     mark(ctx, ST_RAND);
     if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux, dith_f32))) return rc;

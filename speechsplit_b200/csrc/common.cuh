@@ -57,15 +57,15 @@ struct ssfe_ctx {
     ssfe_ctx *lane[kHostLanes] = {};                          // (full contexts, created on first use)
     cudaEvent_t ev_dith_free = nullptr;                       // recorded after the kernel that reads `dith`
     cudaEvent_t ev_mt_go = nullptr;                           // recorded where the dither walk may start
-    bool mt_go_at_start = true;                               // ... at the start of its own call (api.cu), not beside the previous call's rapt_stat
+    bool mt_go_at_start = false;                              // true: only once its own call has started (A/B hook, api.cu)
     char *aux_host[2] = {nullptr, nullptr}, *aux_dev[2] = {nullptr, nullptr};   // side-stream metadata staging
     size_t aux_cap[2] = {0, 0};
     cudaEvent_t aux_free[2] = {nullptr, nullptr};
     int aux_idx = 0;
     bool mt_attr_set = false;
     // MT19937 jump-ahead tap lists (mt19937.cu): slot + 1 per (level, digit), 0 = not built yet
-    int mt_slot[3][256] = {};
-    int mt_cnt[3][256] = {};
+    int mt_slot[5][3][256] = {};                              // [log2(segment blocks) - 8][level][digit]
+    int mt_cnt[5][3][256] = {};
     uint16_t *mt_taps = nullptr;
     int mt_slots_used = 0, mt_slots_cap = 0;
     ssfe_config cfg;
@@ -82,7 +82,6 @@ struct ssfe_ctx {
     float *d_window = nullptr;         // periodic Hann(1024)
     float2 *d_tw = nullptr;            // [k1][lane] = exp(-2 pi i lane k1 / 1024)
     ssfe::MelTables mel;
-    double *d_filt = nullptr;          // filtfilt constants (see filtfilt.cu)
     ssfe::RaptTables *rapt = nullptr;
     ssfe::Workspace ws;
     // host staging for ssfe_extract_host
@@ -179,7 +178,7 @@ struct FiltOut {
     double *y = nullptr;             // filtfilt output (may be null when fused outputs requested)
     const double *dith = nullptr;    // dither stream (fixed offsets); wav = y*0.96 + (U-0.5)*1e-6
     bool dith_raw = false;           // dith holds raw MT19937 word pairs (mt_convert.cuh), not doubles
-    bool dith_f32 = false;           // dith holds the finished term float((U - 0.5) * 1e-6), 4 bytes per sample
+    bool dith_f32 = false;           // dith holds one raw generator word per sample (4 bytes; mt_a_to_dither_f32)
     float *wavp = nullptr;           // padded layout base
     const int64_t *seg_off_dev = nullptr;
     float *wav = nullptr;            // flat f32 [fixed offsets]
@@ -194,7 +193,7 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev,
 // launch_on: nullptr / ctx->stream = public path (doubles out); ctx->aux = side stream, raw word pairs
 // out, ordering handled inside (waits for ev_dith_free and ev_mt_go: starts beside the previous call's
 // stationarity kernel).
-// dither_f32 (side-stream path only): float((U - 0.5) * cfg.dither_scale) out instead of raw word pairs.
+// dither_f32 (side-stream path only): one raw word per double out (4 bytes) instead of the raw word pair.
 int rand_run(ssfe_ctx *ctx, const uint32_t *seeds, const uint64_t *skip, const int64_t *out_off,
              int n, double *u_dev, cudaStream_t launch_on = nullptr, bool dither_f32 = false);
 

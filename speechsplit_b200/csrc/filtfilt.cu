@@ -11,38 +11,38 @@
 // The order-5 recurrence is sequential in time.  It is evaluated as a chunked parallel scan:
 //   1. local : one thread per 256-sample chunk runs the recurrence from a ZERO state and keeps
 //              only the final state s_c (5 doubles);
-//   2. carry : per utterance, z_in[c+1] = A^256 z_in[c] + s_c.  The companion matrix A of this
-//              filter is violently non-normal (poles 0.988..0.996, max |A^k| ~ 1e8 at k ~ 256),
-//              so the carry is done in double-double arithmetic with A^256 computed in
-//              __float128 on the host (filt_consts.cpp); in plain fp64 the scan loses all digits;
-//   3. final : one thread per chunk re-runs the recurrence from its true z_in and writes outputs,
-//              with exactly scipy's operation order ((z[i+1] + x*b) - y*a, no FMA contraction).
+//   2. carry : per utterance, z_in[c+1] = M z_in[c] + s_c with M = A^256;
+//   3. final : one thread per chunk re-runs the recurrence from its true z_in and writes outputs.
+// scipy's own realisation - one DF2T recurrence over (b, a) - cannot be chunked like this without leaving a
+// trace: its state matrix has max |A^k| ~ 1e8, every rounding is amplified accordingly, and although the
+// resulting error (~1e-7) is no larger than scipy's own, it RESTARTS at every chunk boundary - a 62.5 Hz
+// sawtooth whose harmonics reach the first mel bands (filt_consts.cpp has the measurements).  The scan
+// therefore evaluates the same transfer function and the same initial condition as a cascade of one
+// first-order and two second-order sections (constants from filt_consts.cpp, 113-bit algebra): well
+// conditioned, plain fp64 with FMAs, exact response of (b, a, zi) to ~1e-10; what remains against
+// scipy.signal.filtfilt is scipy's own fp64 wobble (<= ~4e-7, below 30 Hz).
 // The backward pass fuses the dither combine and scatters wav (f32) into the padded segment
-// layout the STFT kernel reads.  scipy's own sequential fp64 result carries ~2e-7 of low-frequency
-// round-off (measured against exact arithmetic); the scan agrees with it to that level.
-// filtfilt_mode 1 runs one thread per utterance (chunk = whole signal): a validation aid.
+// layout the STFT kernel reads.
+// filtfilt_mode 1 runs one thread per utterance with scipy's recurrence in scipy's operation order
+// ((z[i+1] + x*b) - y*a, no FMA contraction): bit-identical to scipy, a validation aid.
 #include "common.cuh"
 #include "mt_convert.cuh"
 #include <algorithm>
 
 namespace ssfe {
 
-extern "C" void ssfe_filt_power_dd(const double *a6, int power, double *hi25, double *lo25);   // filt_consts.cpp
-extern "C" void ssfe_filt_power_table_dd(const double *a6, int base, int count, double *out);
+extern "C" int ssfe_filt_cascade(const double *b6, const double *a6, const double *zi5, int chunk, double *sec,
+                                 double *zic, double *m);     // filt_consts.cpp
 
 constexpr int kChunk = 256;
 constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
 constexpr int kFiltThreads = 128;
-// Utterances of at least this many chunks (>= 16.4 s) take the warp-parallel carry, shorter ones the
-// five-lanes-per-utterance carry: the scan does 7x the arithmetic, which only pays when the chain is
-// long (a 500-chunk utterance takes ~56 us in the lane-group kernel, 160 us in the scan).
-// The rule depends on the utterance alone, never on the batch, so results stay batch independent.
-constexpr int kWarpCarryMin = 1024;
-
 
 struct FiltConsts {
-    double b[6], a[6], zi[5];
-    double m_hi[25], m_lo[25];    // A^kChunk, row-major, double-double
+    double b[6], a[6], zi[5];     // scipy's realisation (sequential validation mode)
+    double sec[15];               // cascade sections [3][b0, b1, b2, a1, a2] (section 0 is first order)
+    double zic[5];                // cascade state equivalent to zi
+    double mc[25];                // A_c^kChunk, row-major
     double wav_scale, dither_scale;
 };
 
@@ -66,7 +66,7 @@ struct FiltParams {
     double *wav64;
     double *y1_out;               // forward pass output (extended)
     int dith_raw;                 // dith holds raw MT19937 word pairs
-    int dith_f32;                 // dith holds float((U - 0.5) * 1e-6), already scaled (mt_convert.cuh)
+    int dith_f32;                 // dith holds ONE raw MT19937 word per sample (mt_convert.cuh: mt_a_to_dither_f32)
 };
 
 __constant__ FiltConsts c_filt;
@@ -131,15 +131,17 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
     const bool last_chunk = (j1 == M);
     if (!FINAL && last_chunk) return;        // nobody consumes the carry out of the last chunk
 
+    const int64_t xbase = p.in_off[u];
+    const double *y1 = p.y1 + ebase;
     Df2t f;
     if (FINAL) {
-        const double *s = p.zin + static_cast<int64_t>(g) * 5;
-        f.z0 = s[0]; f.z1 = s[1]; f.z2 = s[2]; f.z3 = s[3]; f.z4 = s[4];
+        // sequential mode: the chunk is the whole utterance and starts from scipy's  zi * x[0]
+        const double x0 = (PASS == 0) ? ext_sample<DTYPE>(p.x, xbase, L, Lf, 0) : y1[M - 1];
+        f.z0 = __dmul_rn(c_filt.zi[0], x0); f.z1 = __dmul_rn(c_filt.zi[1], x0); f.z2 = __dmul_rn(c_filt.zi[2], x0);
+        f.z3 = __dmul_rn(c_filt.zi[3], x0); f.z4 = __dmul_rn(c_filt.zi[4], x0);
     } else {
         f.z0 = f.z1 = f.z2 = f.z3 = f.z4 = 0.0;
     }
-    const int64_t xbase = p.in_off[u];
-    const double *y1 = p.y1 + ebase;
     for (int64_t j = j0; j < j1; ++j) {
         double xin;
         if (PASS == 0) xin = ext_sample<DTYPE>(p.x, xbase, L, Lf, j);
@@ -155,7 +157,8 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
                     if (p.dith) {
                         double d;
                         if (p.dith_f32) {
-                            d = static_cast<double>(reinterpret_cast<const float *>(p.dith)[fbase + nidx]);
+                            d = static_cast<double>(mt_a_to_dither_f32(reinterpret_cast<const uint32_t *>(p.dith)[fbase + nidx],
+                                                                       static_cast<float>(c_filt.dither_scale)));
                         } else {
                             const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(p.dith)[fbase + nidx])
                                                          : p.dith[fbase + nidx];
@@ -187,18 +190,21 @@ constexpr int kTileW = 32;                   // samples per row and sub-step
 constexpr int kTileStride = kTileW + 1;      // doubles per tile row (column reads are conflict-free)
 constexpr int kFiltWarps = 4;
 
-// the local pass only feeds the carry, so it may use fused multiply-adds (11 instead of 21 fp64 ops)
-struct Df2tFused {
-    double z0, z1, z2, z3, z4;
-    __device__ __forceinline__ void step(double x)
+// The cascade the scan runs (see the file header): 13 fp64 operations per sample, FMAs allowed.
+struct Casc {
+    double s0, s1, s2, s3, s4;
+    __device__ __forceinline__ double step(double x)
     {
-        const FiltConsts &c = c_filt;
-        const double y = fma(c.b[0], x, z0);
-        z0 = fma(-c.a[1], y, fma(c.b[1], x, z1));
-        z1 = fma(-c.a[2], y, fma(c.b[2], x, z2));
-        z2 = fma(-c.a[3], y, fma(c.b[3], x, z3));
-        z3 = fma(-c.a[4], y, fma(c.b[4], x, z4));
-        z4 = fma(-c.a[5], y, c.b[5] * x);
+        const double *c = c_filt.sec;
+        const double y0 = fma(c[0], x, s0);                   // section 0: (b0 + b1 z^-1) / (1 + a1 z^-1)
+        s0 = fma(-c[3], y0, c[1] * x);
+        const double y1 = fma(c[5], y0, s1);                  // section 1
+        s1 = fma(-c[8], y1, fma(c[6], y0, s2));
+        s2 = fma(-c[9], y1, c[7] * y0);
+        const double y2 = fma(c[10], y1, s3);                 // section 2
+        s3 = fma(-c[13], y2, fma(c[11], y1, s4));
+        s4 = fma(-c[14], y2, c[12] * y1);
+        return y2;
     }
 };
 
@@ -234,15 +240,11 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
     const bool run = have && (FINAL || !last_chunk);           // nobody consumes the carry of the last chunk
     const int64_t g = static_cast<int64_t>(p.chunk_off[u]) + c;
 
-    Df2t f;
-    Df2tFused ff;
-    if (FINAL) {
-        if (have) {
-            const double *s = p.zin + g * 5;
-            f.z0 = s[0]; f.z1 = s[1]; f.z2 = s[2]; f.z3 = s[3]; f.z4 = s[4];
-        }
-    } else {
-        ff.z0 = ff.z1 = ff.z2 = ff.z3 = ff.z4 = 0.0;
+    Casc f;
+    f.s0 = f.s1 = f.s2 = f.s3 = f.s4 = 0.0;
+    if (FINAL && have) {
+        const double *s = p.zin + g * 5;
+        f.s0 = s[0]; f.s1 = s[1]; f.s2 = s[2]; f.s3 = s[3]; f.s4 = s[4];
     }
     // The forward result travels to the backward pass as FLOAT (8.4 instead of 16.7 GB written once and read
     // twice for the VCTK-shaped corpus).  The backward pass then filters exactly that rounded signal - both its
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
     // by <= 2.6e-7, the size of scipy's own fp64 round-off for this filter and inside the 1e-6 bar.
     const float *y1 = (PASS == 1) ? p.y1f + ebase : nullptr;
     float *y1o = (FINAL && PASS == 0) ? p.y1f_out + ebase : nullptr;
-    const float *dith = (FINAL && PASS == 1 && p.dith && p.dith_f32) ? reinterpret_cast<const float *>(p.dith) + fbase : nullptr;
+    const uint32_t *dith = (FINAL && PASS == 1 && p.dith && p.dith_f32) ? reinterpret_cast<const uint32_t *>(p.dith) + fbase : nullptr;
+    const float dscale = static_cast<float>(c_filt.dither_scale);
     const double *dith_gen = (FINAL && PASS == 1 && p.dith && !p.dith_f32) ? p.dith + fbase : nullptr;
     float *wavp = (FINAL && PASS == 1 && p.wavp) ? p.wavp + p.seg_off[u] + kHalfPad : nullptr;
     // ---- load machinery -------------------------------------------------------------------------------
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
                 for (int i = 0; i < cnt; ++i) row[i] = f.step(row[i]);
             } else {
 #pragma unroll 4
-                for (int i = 0; i < cnt; ++i) ff.step(row[i]);
+                for (int i = 0; i < cnt; ++i) f.step(row[i]);
             }
         }
         __syncwarp();
@@ -367,23 +370,25 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
                 for (int r = 0; r < 32; ++r) y1o[jsub + r * kChunk + lane] = static_cast<float>(tl[r * kTileStride + lane]);
             } else if (fast_out) {
                 // production path of the backward pass: wav = y * 0.96 + (U - 0.5) * 1e-06 -> f32 segment; the
-                // dither term arrives finished, as float (mt_walk_kernel<true>).  These loads were the kernel's
-                // largest stall when they were 8-byte raw word pairs (55 % of the samples); staging them with
-                // cp.async (8 KB of shared memory per warp) during the recurrence was measured then: 3 CTAs per SM
-                // instead of 4, and the pass got 4.5 ms SLOWER on the full corpus.
+                // dither arrives as one raw generator word per sample (mt_walk_kernel<true>), tempering and the
+                // float conversion happen here, where issue slots are idle (the kernel waits for memory).  These
+                // loads were the kernel's largest stall when they were 8-byte word pairs (55 % of the samples);
+                // staging them with cp.async (8 KB of shared memory per warp) during the recurrence was measured
+                // then: 3 CTAs per SM instead of 4, and the pass got 4.5 ms SLOWER on the full corpus.
                 const int n0 = M - 1 - kPadLen - jsub - lane;
-                const float *dr = dith + n0;
-                float dv[32];
+                const uint32_t *dr = dith + n0;
+                uint32_t dv[32];
 #pragma unroll
                 for (int r = 0; r < 32; ++r) dv[r] = dr[-r * kChunk];
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     const double y = tl[r * kTileStride + lane];
-                    wavp[n0 - r * kChunk] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(dv[r])));
+                    wavp[n0 - r * kChunk] = static_cast<float>(
+                        __dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(mt_a_to_dither_f32(dv[r], dscale))));
                 }
             } else if (PASS == 1 && dith && wavp && !p.y && !p.wav && !p.wav64) {
-                // edge tile of the production path: same combine, dither terms fetched together
-                float dv[32];
+                // edge tile of the production path: same combine, dither words fetched together
+                uint32_t dv[32];
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     const int nidx = M - 1 - kPadLen - (jsub + r * kChunk + lane);
@@ -395,7 +400,8 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
                     const int nidx = M - 1 - kPadLen - j;
                     if (r < rows && j < M && nidx >= 0 && nidx < Lf) {
                         const double y = tl[r * kTileStride + lane];
-                        wavp[nidx] = static_cast<float>(__dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(dv[r])));
+                        wavp[nidx] = static_cast<float>(
+                            __dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(mt_a_to_dither_f32(dv[r], dscale))));
                     }
                 }
             } else {
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
                             if (dith || dith_gen) {
                                 double d;
                                 if (dith) {
-                                    d = static_cast<double>(dith[nidx]);
+                                    d = static_cast<double>(mt_a_to_dither_f32(dith[nidx], dscale));
                                 } else {
                                     const double uu = p.dith_raw ? mt_raw_to_double(reinterpret_cast<const uint2 *>(dith_gen)[nidx]) : dith_gen[nidx];
                                     d = __dmul_rn(__dsub_rn(uu, 0.5), c_filt.dither_scale);
@@ -432,140 +438,24 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
     }
     if (!FINAL && run) {
         double *s = p.state + g * 5;
-        s[0] = ff.z0; s[1] = ff.z1; s[2] = ff.z2; s[3] = ff.z3; s[4] = ff.z4;
+        s[0] = f.s0; s[1] = f.s1; s[2] = f.s2; s[3] = f.s3; s[4] = f.s4;
     }
 }
 
-// ---- double-double helpers for the carry -------------------------------------------------------
-struct dd {
-    double hi, lo;
-};
-__device__ __forceinline__ dd dd_two_sum(double a, double b)
-{
-    const double s = __dadd_rn(a, b);
-    const double bb = __dsub_rn(s, a);
-    const double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
-    return {s, e};
-}
-// "sloppy" double-double sum (Dekker): error ~ 2^-104 relative to |a|+|b|, half the dependent depth of
-// the IEEE-style version; the carry only needs ~2^-80
-__device__ __forceinline__ dd dd_add(dd a, dd b)
-{
-    const dd s = dd_two_sum(a.hi, b.hi);
-    const double e = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
-    const double hi = __dadd_rn(s.hi, e);
-    return {hi, __dsub_rn(e, __dsub_rn(hi, s.hi))};
-}
-__device__ __forceinline__ dd dd_mul(dd a, dd b)
-{
-    const double p = __dmul_rn(a.hi, b.hi);
-    double e = __fma_rn(a.hi, b.hi, -p);
-    e = __fma_rn(a.hi, b.lo, e);
-    e = __fma_rn(a.lo, b.hi, e);
-    const double hi = __dadd_rn(p, e);
-    return {hi, __dsub_rn(e, __dsub_rn(hi, p))};
-}
-
-__device__ __forceinline__ dd dd_shfl(dd v, int src)
-{
-    return {__shfl_sync(0xffffffffu, v.hi, src), __shfl_sync(0xffffffffu, v.lo, src)};
-}
-__device__ __forceinline__ dd dd_shfl_up(dd v, int d)
-{
-    return {__shfl_up_sync(0xffffffffu, v.hi, d), __shfl_up_sync(0xffffffffu, v.lo, d)};
-}
-
-// Turn the zero-state finals into true chunk-entry states: z' = M z + s per chunk, M = A^256 in
-// double-double.  FIVE LANES PER UTTERANCE: lane r owns state component r and computes row r of the
-// mat-vec (the other four components arrive by shuffle), six utterances per warp.  Per row the
-// arithmetic and its order are exactly those of a one-thread version - five products, summed as a
-// tree with the chunk's zero-state final - so the result does not depend on how utterances are packed;
-// but the chain per chunk is one row deep instead of five, and a batch of a few thousand utterances
-// (one GPU of eight) spreads over 6x more warps: 0.34 ms -> 0.05 ms per pass at 5 600 utterances.
-constexpr int kCarryGroup = 5, kCarryPerWarp = 6, kCarryThreads = 128;
+// ---- carry ---------------------------------------------------------------------------------------------
+// Turn the zero-state finals into true chunk-entry states: z' = M z + s per chunk, M = A_c^256 of the cascade.
+// Its entries are O(10) and the recurrence is well conditioned, so this is plain fp64 (the DF2T realisation
+// needed double-double here, five lanes per utterance and a warp-wide scan for long utterances).  One thread
+// per utterance; the zero-state final of the next chunk is fetched while this chunk's update is computed.
+// A 3 s utterance is 188 steps of a five-deep FMA chain (~6 us), a 60 s one 3 751 (~0.12 ms).
+constexpr int kCarryThreads = 64;
 
 template <int DTYPE, int PASS>
 __global__ void __launch_bounds__(kCarryThreads) filt_carry_kernel(const FiltParams p)
 {
-    const int lane = threadIdx.x & 31, grp = lane / kCarryGroup, r = lane - kCarryGroup * grp;
-    const int warp = (blockIdx.x * kCarryThreads + threadIdx.x) >> 5;
-    const int u = warp * kCarryPerWarp + grp;
-    const bool live = grp < kCarryPerWarp && u < p.n;
-    int c0 = 0, nc = 0;
-    double x0 = 0.0;
-    if (live) {
-        c0 = p.chunk_off[u];
-        nc = p.chunk_off[u + 1] - c0;
-        if (p.chunk_len == kChunk && nc >= kWarpCarryMin) nc = 0;      // long utterances: filt_carry_warp_kernel
-    }
-    if (live && nc > 0) {
-        const int64_t L = p.in_off[u + 1] - p.in_off[u];
-        const int64_t fbase = p.fix_off[u];
-        const int64_t Lf = p.fix_off[u + 1] - fbase;
-        const int64_t M = Lf + 2 * kPadLen;
-        const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
-        if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
-        else x0 = p.y1f ? static_cast<double>(p.y1f[ebase + M - 1]) : p.y1[ebase + M - 1];
-    }
-    const int nmax = __reduce_max_sync(0xffffffffu, nc);
-    const int rr = min(r, 4);
-    dd z = {__dmul_rn(c_filt.zi[rr], x0), 0.0};
-    dd mrow[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) mrow[k] = {c_filt.m_hi[rr * 5 + k], c_filt.m_lo[rr * 5 + k]};
-    // the zero-state final of the NEXT chunk is fetched while this chunk's update is computed
-    const double *__restrict__ s_in = p.state + static_cast<int64_t>(c0) * 5 + rr;
-    double *__restrict__ zout = p.zin + static_cast<int64_t>(c0) * 5 + rr;
-    double nx = (nc > 1) ? s_in[0] : 0.0;
-    const int src0 = min(kCarryGroup * grp, 27);
-    for (int c = 0; c < nmax; ++c) {
-        const double sc = nx;
-        if (c < nc) zout[c * 5] = z.hi;                // z_in of this chunk (hi + lo rounds to hi)
-        if (c + 2 < nc) nx = s_in[(c + 1) * 5];         // (the last chunk has no zero-state final)
-        dd pr[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) pr[k] = dd_mul(mrow[k], dd_shfl(z, src0 + k));
-        if (c + 1 < nc) {
-            // the five products are summed as a tree, not a chain
-            const dd s01 = dd_add(pr[0], pr[1]), s23 = dd_add(pr[2], pr[3]);
-            const dd s4c = dd_add(pr[4], dd{sc, 0.0});
-            z = dd_add(dd_add(s01, s23), s4c);
-        }
-    }
-}
-
-// ---- warp-parallel carry ----------------------------------------------------------------------------
-// The lane-group carry above is one latency chain of (chunks) double-double mat-vecs: 188 for
-// a 3 s utterance, 3751 for a 60 s one (26 ms per pass).  Here a WARP owns an utterance: lane = chunk
-// inside a tile of 32, and the recurrence z[c+1] = M z[c] + s[c] (M = A^256) is solved per tile by a
-// Kogge-Stone scan over the lanes with the precomputed powers P[j] = M^j, j = 1..32 (double-double,
-// formed in __float128 on the host):
-//     v[c] <- v[c] + P[d] v[c-d]   for d = 1, 2, 4, 8, 16       ->  v[c] = sum_{i<=c} M^(c-i) s[i]
-//     z_in[c] = P[c] z0 + v[c-1]   (z_in[0] = z0),   next tile's z0 = P[32] z0 + v[31]
-// 7 mat-vecs of depth per tile instead of 32, and no dependence on the batch: the same utterance gives
-// bit-identical results in any batch (the strategy is fixed, not chosen by batch size).
-__device__ __forceinline__ void dd_matvec(const double *__restrict__ P, const dd (&z)[5], dd (&out)[5])
-{
-    // P: [2][25] (hi then lo), row-major
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        dd pr[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) pr[k] = dd_mul(dd{P[i * 5 + k], P[25 + i * 5 + k]}, z[k]);
-        out[i] = dd_add(dd_add(dd_add(pr[0], pr[1]), dd_add(pr[2], pr[3])), pr[4]);
-    }
-}
-constexpr int kCarryWarps = 4;
-
-template <int DTYPE, int PASS>
-__global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_warp_kernel(const FiltParams p,
-                                                                           const double *__restrict__ pw /* [33][50] */)
-{
-    const int lane = threadIdx.x & 31;
-    const int u = blockIdx.x * kCarryWarps + (threadIdx.x >> 5);
+    const int u = blockIdx.x * kCarryThreads + threadIdx.x;
     if (u >= p.n) return;
     const int c0 = p.chunk_off[u], nc = p.chunk_off[u + 1] - c0;
-    if (nc < kWarpCarryMin) return;
     const int64_t L = p.in_off[u + 1] - p.in_off[u];
     const int64_t fbase = p.fix_off[u];
     const int64_t Lf = p.fix_off[u + 1] - fbase;
@@ -573,50 +463,41 @@ __global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_warp_kernel(const
     const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
     double x0;
     if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
-    else x0 = p.y1f ? static_cast<double>(p.y1f[ebase + M - 1]) : p.y1[ebase + M - 1];
-    dd z0[5];
+    else x0 = static_cast<double>(p.y1f[ebase + M - 1]);
+    double z[5], nx[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) z0[i] = {__dmul_rn(c_filt.zi[i], x0), 0.0};
+    for (int i = 0; i < 5; ++i) {
+        z[i] = c_filt.zic[i] * x0;                       // scipy's zi * x[0], in cascade coordinates
+        nx[i] = 0.0;
+    }
     const double *__restrict__ s_in = p.state + static_cast<int64_t>(c0) * 5;
     double *__restrict__ zout = p.zin + static_cast<int64_t>(c0) * 5;
-
-    for (int t0 = 0; t0 < nc; t0 += 32) {
-        const int c = t0 + lane;
-        dd v[5];
+    if (nc > 1) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) v[i] = {(c + 1 < nc) ? s_in[c * 5 + i] : 0.0, 0.0};   // last chunk: no final
-        // inclusive scan over the tile
+        for (int i = 0; i < 5; ++i) nx[i] = s_in[i];
+    }
+    for (int c = 0; c < nc; ++c) {
+        double sc[5];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            dd up[5], mv[5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) up[i] = dd_shfl_up(v[i], d);
-            dd_matvec(pw + d * 50, up, mv);
-            if (lane >= d) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) v[i] = dd_add(v[i], mv[i]);
-            }
+        for (int i = 0; i < 5; ++i) {
+            sc[i] = nx[i];
+            zout[c * 5 + i] = z[i];                      // z_in of this chunk
         }
-        // chunk-entry states
-        dd e[5], pz[5];
+        if (c + 2 < nc) {                                // (the last chunk has no zero-state final)
 #pragma unroll
-        for (int i = 0; i < 5; ++i) e[i] = dd_shfl_up(v[i], 1);
-        dd_matvec(pw + max(lane, 1) * 50, z0, pz);
-        if (c < nc) {
+            for (int i = 0; i < 5; ++i) nx[i] = s_in[(c + 1) * 5 + i];
+        }
+        if (c + 1 < nc) {
+            double t[5];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                const dd zi = (lane == 0) ? z0[i] : dd_add(pz[i], e[i]);
-                zout[c * 5 + i] = zi.hi;
+                double acc = sc[i];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) acc = fma(c_filt.mc[i * 5 + k], z[k], acc);
+                t[i] = acc;
             }
-        }
-        // carry into the next tile
-        if (t0 + 32 < nc) {
-            dd last[5], nz[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) last[i] = dd_shfl(v[i], 31);
-            dd_matvec(pw + 32 * 50, z0, nz);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) z0[i] = dd_add(nz[i], last[i]);
+            for (int i = 0; i < 5; ++i) z[i] = t[i];
         }
     }
 }
@@ -650,41 +531,35 @@ int fill_reflect_edges(ssfe_ctx *ctx, float *wavp, const int64_t *seg_off_dev, c
 
 template <int DTYPE>
 static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEvent_t dith_ready,
-                          const int *tile_off, int n_tiles, const int *tile_map, bool any_long)
+                          const int *tile_off, int n_tiles, const int *tile_map)
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
-    const unsigned gu = (p.n + kCarryPerWarp * (kCarryThreads / 32) - 1) / (kCarryPerWarp * (kCarryThreads / 32));
+    const unsigned gu = (p.n + kCarryThreads - 1) / kCarryThreads;
     cudaStream_t st = ctx->stream;
-    if (!sequential) {
-        filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    if (sequential) {
+        filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
         SSFE_LAUNCHED(ctx);
+        p.y1 = p.y1_out;
+        if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));
+        filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
+        SSFE_LAUNCHED(ctx);
+        if (dith_ready) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));
+        return SSFE_OK;
     }
-    const unsigned gw = (p.n + kCarryWarps - 1) / kCarryWarps;
+    filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    SSFE_LAUNCHED(ctx);
     filt_carry_kernel<DTYPE, 0><<<gu, kCarryThreads, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
-    if (!sequential && any_long) {
-        filt_carry_warp_kernel<DTYPE, 0><<<gw, kCarryWarps * 32, 0, st>>>(p, ctx->d_filt);
-        SSFE_LAUNCHED(ctx);
-    }
-    if (sequential) filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
-    else filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
-    if (sequential) p.y1 = p.y1_out;
-    else p.y1f = p.y1f_out;
-    if (!sequential) {
-        filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
-        SSFE_LAUNCHED(ctx);
-    }
+    p.y1f = p.y1f_out;
+    filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    SSFE_LAUNCHED(ctx);
     filt_carry_kernel<DTYPE, 1><<<gu, kCarryThreads, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
-    if (!sequential && any_long) {
-        filt_carry_warp_kernel<DTYPE, 1><<<gw, kCarryWarps * 32, 0, st>>>(p, ctx->d_filt);
-        SSFE_LAUNCHED(ctx);
-    }
     if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
-    if (sequential) filt_chunk_kernel<DTYPE, 1, true><<<gc, kFiltThreads, 0, st>>>(p);
-    else filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     if (dith_ready) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));   // the dither buffer may be refilled
     return SSFE_OK;
@@ -697,7 +572,6 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     const bool sequential = ctx->cfg.filtfilt_mode == 1;
     std::vector<int> chunk_off(n + 1), tile_off(n + 1);
     int64_t chunks = 0, max_m = 0, tiles = 0;
-    bool any_long = false;
     for (int i = 0; i < n; ++i) {
         const int64_t Lf = fix_off_host[i + 1] - fix_off_host[i];
         if (Lf <= kPadLen)
@@ -709,7 +583,6 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
         chunk_off[i] = static_cast<int>(chunks);
         tile_off[i] = static_cast<int>(tiles);
         const int64_t nc = sequential ? 1 : (M + kChunk - 1) / kChunk;
-        any_long = any_long || nc >= kWarpCarryMin;
         chunks += nc;
         tiles += (nc + 31) / 32;
         if (chunks > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (chunks)");
@@ -758,9 +631,9 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.y1_out = sequential ? static_cast<double *>(ctx->ws.y1.p) : nullptr;
     p.y1f_out = sequential ? nullptr : static_cast<float *>(ctx->ws.y1.p);
     switch (dtype) {
-    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
-    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
-    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map, any_long);
+    case SSFE_F32: return filtfilt_typed<SSFE_F32>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map);
+    case SSFE_F64: return filtfilt_typed<SSFE_F64>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map);
+    case SSFE_I16: return filtfilt_typed<SSFE_I16>(ctx, p, sequential, out.dith_ready, d_tile_off, n_tiles, d_tile_map);
     default: return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: unknown dtype %d", dtype);
     }
 }
@@ -774,12 +647,12 @@ int init_filtfilt(ssfe_ctx *ctx)
         c.a[i] = ctx->cfg.a[i] / ctx->cfg.a[0];
     }
     for (int i = 0; i < 5; ++i) c.zi[i] = ctx->cfg.zi[i];
-    ssfe_filt_power_dd(c.a, kChunk, c.m_hi, c.m_lo);
-    {   // P[j] = A^(kChunk * j), j = 1..32, for the warp-parallel carry
-        std::vector<double> pw(33 * 50, 0.0);
-        ssfe_filt_power_table_dd(c.a, kChunk, 32, pw.data());
-        SSFE_CUDA(ctx, cudaMalloc(&ctx->d_filt, pw.size() * sizeof(double)));
-        SSFE_CUDA(ctx, cudaMemcpy(ctx->d_filt, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        const int rc = ssfe_filt_cascade(c.b, c.a, c.zi, kChunk, c.sec, c.zic, c.mc);
+        if (rc != 0)
+            return set_error(ctx, SSFE_ERR_INVALID,
+                             "filtfilt: the filter (b, a) does not factor into one first-order and two second-order stable "
+                             "sections (code %d); only filtfilt_mode = 1 could run it", rc);
     }
     c.wav_scale = ctx->cfg.wav_scale;
     c.dither_scale = ctx->cfg.dither_scale;
@@ -789,8 +662,7 @@ int init_filtfilt(ssfe_ctx *ctx)
 
 void free_filtfilt(ssfe_ctx *ctx)
 {
-    cudaFree(ctx->d_filt);
-    ctx->d_filt = nullptr;
+    (void)ctx;
 }
 
 }  // namespace ssfe

@@ -1345,8 +1345,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles, cand_map);
         SSFE_LAUNCHED(ctx);
         mark(ctx, ST_RAPT_STAT);
-        // (mt_go_at_start == false, the earlier schedule:) the next call's dither generation (side stream, high
-        // priority) may start here, beside the stationarity kernel - see extract_device for why it no longer does.
+        // the next call's dither generation (side stream, high priority) may start here, beside the stationarity
+        // kernel (extract_device has the measurements)
         if (!ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
         rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles, stat_map);
         SSFE_LAUNCHED(ctx);
