@@ -293,7 +293,8 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
     free_rapt(ctx);
     Workspace &w = ctx->ws;
     DevBuf *all[] = {&w.wavp, &w.y1, &w.dith, &w.meta_dev, &w.tiles, &w.misc, &w.rapt_ds, &w.rapt_cand,
-                     &w.rapt_stat, &w.rapt_f0, &w.dec_map, &w.cand_map, &w.stat_map, &w.filt_map, &w.carry, &w.mt_state, &w.mt_state_aux, &ctx->h_x, &ctx->h_mel, &ctx->h_f0, &ctx->h_bins};
+                     &w.rapt_stat, &w.rapt_f0, &w.dec_map, &w.cand_map, &w.stat_map, &w.filt_map, &w.carry, &w.mt_state, &w.mt_state_aux, &ctx->h_x, &ctx->h_mel, &ctx->h_f0, &ctx->h_bins,
+                     &ctx->h_dith};
     for (DevBuf *b : all) free_buf(*b);
     if (ctx->mt_taps) cudaFree(ctx->mt_taps);
     if (ctx->meta_host) cudaFreeHost(ctx->meta_host);
@@ -306,7 +307,8 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
         for (cudaEvent_t e : row)
             if (e) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
-    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1]})
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1],
+                          ctx->ev_hd_ready[0], ctx->ev_hd_ready[1]})
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < ssfe_ctx::kHostSlots; ++i)
         for (cudaEvent_t e : {ctx->ev_h2d[i], ctx->ev_comp[i], ctx->ev_d2h[i]})
@@ -436,16 +438,17 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     int rc;
     if ((rc = check_ranges(ctx, b->f0_lo, b->f0_hi, n))) return rc;
     if ((rc = ensure(ctx, ctx->ws.wavp, (pos + kSegSlack) * sizeof(float)))) return rc;
-    if ((rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
+    const bool ext_dith = ctx->ext_dith != nullptr;          // ssfe_extract_host generated it for the whole call
+    if (!ext_dith && (rc = ensure(ctx, ctx->ws.dith, fix[n] * sizeof(double)))) return rc;
     float *wavp = static_cast<float *>(ctx->ws.wavp.p);
-    double *dith = static_cast<double *>(ctx->ws.dith.p);
+    double *dith = ext_dith ? static_cast<double *>(const_cast<void *>(ctx->ext_dith)) : static_cast<double *>(ctx->ws.dith.p);
 
     // the dither stream is independent of the signal until the very last filtfilt kernel: generate
     // it on a side stream while the forward / backward-local passes run
     // Production path: the generator leaves one raw word per sample (4 bytes; the float dither term is formed from
     // its 27 random bits in the consumer, mt_convert.cuh).  The validation paths - sequential filter mode, or a
     // caller asking for the fp64 wav - keep the raw word pairs and convert bit for bit to numpy's doubles.
-    const bool dith_f32 = ctx->cfg.filtfilt_mode != 1 && !o->wav64;
+    const bool dith_f32 = ext_dith || (ctx->cfg.filtfilt_mode != 1 && !o->wav64);
     // Where the side stream may start: by default beside the PREVIOUS call's stationarity kernel (rapt_run records
     // ev_mt_go there), i.e. as early as the dither buffer is free.  For a large batch it makes no difference where
     // the generator's ~2 G warp instructions run - measured on the full corpus: rapt_stat 18.9 + filtfilt 17.8 ms
@@ -454,7 +457,7 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     // hide behind, and the head start covers it.  SSFE_MT_GO=start forces the late start (A/B hook).
     if (ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, ctx->stream));
     mark(ctx, ST_RAND);
-    if ((rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux, dith_f32))) return rc;
+    if (!ext_dith && (rc = rand_run(ctx, b->spk_seed, b->dither_skip, fix.data(), n, dith, ctx->aux, dith_f32))) return rc;
     mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
@@ -465,7 +468,7 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     fo.seg_off_dev = d_seg;
     fo.wav = o->wav;
     fo.wav64 = o->wav64;
-    fo.dith_ready = ctx->ev_join;
+    fo.dith_ready = ext_dith ? ctx->ext_dith_ready : ctx->ev_join;
     fo.dith_raw = !dith_f32;
     fo.dith_f32 = dith_f32;
     if ((rc = filtfilt_run(ctx, x_dev, dtype, b->sample_offsets, fix.data(), n, fo))) return rc;
@@ -540,16 +543,25 @@ static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void 
                                                          : std::min<int64_t>(std::max<int64_t>(total_samples / 8, 16LL << 20), 256LL << 20);
     std::vector<int64_t> targets;
     {
-        // ramp up (T/8, T/8, T/4, T/4, T/2, T/2), full sub-batches, ramp down (T/2, T/4); a remainder too
-        // small to stand alone is merged into the first ramp-down sub-batch
-        int64_t remaining = b->sample_offsets[n] - b->sample_offsets[0];
-        const int64_t T = std::max<int64_t>(kChunkSamples, 8), down_sum = T / 2 + T / 4;
+        // ramp up (T/8, T/8, T/4, T/4, T/2, T/2), full sub-batches, ramp down (T/2, T/4, T/8, T/16): nothing hides
+        // the kernels and the download of the LAST sub-batch, so it is the smallest (measured on the full corpus:
+        // the tail after the last upload went from 12.7 ms with a T/4 ending to ~5); a remainder too small to stand
+        // alone is merged into the first ramp-down sub-batch
+        int64_t remaining = total_samples;
+        const int64_t T = std::max<int64_t>(kChunkSamples, 16);
+        const int64_t down[4] = {T / 2, T / 4, T / 8, T / 16};
+        const int64_t down_sum = down[0] + down[1] + down[2] + down[3];
         if (remaining <= T / 4) {
             targets.push_back(remaining);
         } else if (remaining <= down_sum + T / 8) {
-            targets.push_back(remaining / 3);
-            targets.push_back(remaining / 3);
-            targets.push_back(remaining - 2 * (remaining / 3));
+            // small call: halves down to a sixteenth
+            int64_t part = remaining / 2;
+            for (int k = 0; k < 3 && remaining - part > (16 << 10); ++k) {
+                targets.push_back(part);
+                remaining -= part;
+                part = remaining / 2;
+            }
+            targets.push_back(remaining);
         } else {
             for (int64_t h : {T / 8, T / 8, T / 4, T / 4, T / 2, T / 2})
                 if (remaining - h >= down_sum) {
@@ -562,8 +574,10 @@ static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void 
             }
             const int64_t rest = remaining - down_sum;          // 0 <= rest < T
             if (rest >= T / 4) targets.push_back(rest);
-            targets.push_back(T / 2 + (rest < T / 4 ? rest : 0));
-            targets.push_back(T / 4);
+            targets.push_back(down[0] + (rest < T / 4 ? rest : 0));
+            targets.push_back(down[1]);
+            targets.push_back(down[2]);
+            targets.push_back(down[3]);
         }
     }
     std::vector<int> cuts{0};
@@ -618,6 +632,25 @@ static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_fork, 0));
     for (int i = 0; i < ssfe_ctx::kHostLanes; ++i) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[i]->stream, ctx->ev_fork, 0));
 
+    // The dither of the whole call is generated here, once, on this context's side stream: one raw word per sample
+    // (mt_convert.cuh) for every utterance, in two groups - the short ramp-up sub-batches first, so that the first
+    // backward filter pass does not wait for the whole corpus.  Generating it per sub-batch in the lanes cost every
+    // sub-batch its own jump kernel (~1 M warp instructions per stream segment, however short the sub-batch) and
+    // made the kernels of a sub-batch wait for a serial segment walk; per call it is 2 + 3.5 ms beside the uploads.
+    const bool hoist = ctx->cfg.filtfilt_mode != 1;
+    const int n_first = std::min(4, n_chunks);                 // sub-batches of the first group
+    if (hoist) {
+        if ((rc = ensure(ctx, ctx->h_dith, static_cast<size_t>(fix[n]) * sizeof(uint32_t)))) return rc;
+        SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        for (int g = 0; g < 2; ++g) {
+            if (!ctx->ev_hd_ready[g]) SSFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_hd_ready[g], cudaEventDisableTiming));
+            const int ua = (g == 0) ? 0 : cuts[n_first], ub = (g == 0) ? cuts[n_first] : n;
+            if (ub > ua && (rc = rand_run(ctx, b->spk_seed + ua, b->dither_skip + ua, fix.data() + ua, ub - ua,
+                                          static_cast<double *>(ctx->h_dith.p), ctx->aux, true)))
+                return rc;
+            SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_hd_ready[g], ctx->aux));
+        }
+    }
     const bool trace = getenv("SSFE_TRACE_HOST") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto tmark = [&](cudaStream_t st) {
@@ -668,6 +701,8 @@ static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         o.f0_norm = d_f0;
         o.bins = d_bins;
         tmark(ln->stream);
+        ln->ext_dith = hoist ? static_cast<const uint32_t *>(ctx->h_dith.p) + fix[u0] : nullptr;
+        ln->ext_dith_ready = hoist ? ctx->ev_hd_ready[c < n_first ? 0 : 1] : nullptr;
         if ((rc = extract_device(ln, &cb, d_x, dtype, &o, cfix, cfoff))) return set_error(ctx, rc, "%s", ln->err);
         SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ln->stream));
         tmark(ln->stream);
@@ -709,6 +744,7 @@ extern "C" int ssfe_extract_host(ssfe_ctx *ctx, const ssfe_batch *b, const void 
         // a sub-batch failed after earlier ones were queued: their uploads read and their downloads write the
         // caller's host buffers, so nothing may be in flight when the error reaches the caller
         cudaStreamSynchronize(ctx->copy_in);
+        cudaStreamSynchronize(ctx->aux);
         for (ssfe_ctx *ln : ctx->lane)
             if (ln) cudaStreamSynchronize(ln->stream);
         cudaStreamSynchronize(ctx->copy_out);

@@ -95,6 +95,12 @@ struct ssfe_ctx {
     void *pin_in = nullptr;  size_t pin_in_cap = 0;
     void *pin_out = nullptr; size_t pin_out_cap = 0;
     ssfe::DevBuf h_x, h_mel, h_f0, h_bins;
+    // ssfe_extract_host generates the dither of the WHOLE call on the main context's side stream (two groups of
+    // sub-batches) and hands every lane a pointer into it (api.cu)
+    ssfe::DevBuf h_dith;
+    cudaEvent_t ev_hd_ready[2] = {nullptr, nullptr};
+    const void *ext_dith = nullptr;                           // lane contexts: dither words of the current sub-batch
+    cudaEvent_t ext_dith_ready = nullptr;
     long long host_chunk_samples = 256LL << 20;               // sub-batch size of ssfe_extract_host when forced (test hook)
     bool host_chunk_forced = false;
 };
