@@ -33,11 +33,10 @@ struct Workspace {
 };
 
 struct MelTables {
-    int n_groups = 0;                  // aligned 4-bin groups per lane (all slots)
-    int slot_end[3] = {0, 0, 0};       // cumulative group count per (slot)
+    int n_groups = 0;                  // aligned 4-bin groups per lane
+    int conflict_cost = 0;             // shared-memory wavefronts per 128-bit load step after the layout search (>= 4 n_groups)
     float4 *w4 = nullptr;              // [n_groups][32] weights (already * 0.5)
-    int *k0 = nullptr;                 // [n_groups][32] first bin of the group
-    int *band = nullptr;               // [3][32] band of (slot, lane), -1 = none
+    int *k0 = nullptr;                 // [n_groups][32] swizzled address | flush flag | band << 16
 };
 
 struct RaptTables;                     // rapt.cu

@@ -912,6 +912,7 @@ constexpr size_t kStatSmem = (4 * kStatWinPairs + kStatXWords + kStatFrames * 20
 // kernel falls back to the exact table (use_log == 0).
 constexpr int kDpWarps = 4;
 constexpr int kMaxLag = 336;
+constexpr int kDpBlk = 16;         // frames per record block of the Viterbi pass (g >> 4 below)
 
 __device__ __forceinline__ float jump_cost(float ftemp, float ln2, float fdouble, float freqwt)
 {
@@ -933,6 +934,11 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
     __shared__ unsigned char s_ring[kDpWarps][kRing][kCMax];
     __shared__ unsigned char s_path[kDpWarps][kRing];
     __shared__ double s_log[kMaxLag];
+    // records of 16 consecutive frames of each warp's utterance (see load_block below)
+    __shared__ __align__(16) float s_bmp[kDpWarps][kDpBlk * kCMax];
+    __shared__ __align__(16) int s_bloc[kDpWarps][kDpBlk * kCMax / 2];
+    __shared__ float s_bsr[kDpWarps][2 * kDpBlk];
+    __shared__ unsigned char s_bnc[kDpWarps][kDpBlk];
     for (int i = threadIdx.x; i < kMaxLag; i += blockDim.x) s_log[i] = p.log_lag[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -952,33 +958,60 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
     double lg_prev = 0.0;
     int head = -1, tail = 0, num_active = 0;
     int my_pre = 0;
-    // software pipeline: records of the next frame
-    int n_nc = 0, n_loc = -1;
-    float n_mp = 0.0f, n_sta = 0.0f, n_rr = 1.0f;
-    // (prefetch.global.L1 of the records eight frames ahead was measured: no gain for one utterance, and the extra
-    // instructions cost the throughput-bound full-corpus launch 0.4 ms)
-    auto fetch = [&](int g) {
-        if (g < ut.n_fr) {
-            const long long gf = ut.fr_off + g;
-            n_nc = p.ncand[gf];
-            n_loc = (lane < kCMax) ? p.loc[gf * kCMax + lane] : -1;
-            n_mp = (lane < kCMax) ? p.mp[gf * kCMax + lane] : 0.0f;
-            n_sta = p.sta[gf];
-            n_rr = p.rr[gf];
-        }
+    // Software pipeline in blocks of kDpBlk = 16 frames: while the frames of block b are processed out of shared
+    // memory, the records of block b + 1 (320 local costs, 320 lags, 16 x stationarity / rms ratio / count) are in
+    // flight into registers, all loads issued together; at the block boundary they are stored to shared memory and
+    // the next block's loads go out.  The first version fetched ONE frame ahead, and a frame (~0.3 us of shuffles
+    // and compares) is shorter than a trip to L2: ncu had a quarter of the stall samples on the first use of the
+    // fetched record, and the pass cost ~1 us per frame - 4.8 ms for a 60 s utterance.
+    // (prefetch.global.L1 eight frames ahead was measured first: no gain.)
+    float *bmp = s_bmp[w];
+    const short *bloc = reinterpret_cast<const short *>(s_bloc[w]);
+    float *bsr = s_bsr[w];
+    unsigned char *bnc = s_bnc[w];
+    float r_mp[kDpBlk * kCMax / 32];
+    int r_loc[kDpBlk * kCMax / 64];
+    float r_sr = 0.0f;
+    int r_nc = 0;
+    auto load_block = [&](int blk) {            // global -> registers (the record arrays have kDpBlk frames of slack)
+        const long long gf0 = ut.fr_off + static_cast<long long>(blk) * kDpBlk;
+        const float *gm = p.mp + gf0 * kCMax;
+        const int *gl = reinterpret_cast<const int *>(p.loc + gf0 * kCMax);
+#pragma unroll
+        for (int k = 0; k < kDpBlk * kCMax / 32; ++k) r_mp[k] = gm[lane + 32 * k];
+#pragma unroll
+        for (int k = 0; k < kDpBlk * kCMax / 64; ++k) r_loc[k] = gl[lane + 32 * k];
+        r_sr = (lane < kDpBlk) ? p.sta[gf0 + lane] : p.rr[gf0 + lane - kDpBlk];
+        r_nc = (lane < kDpBlk) ? p.ncand[gf0 + lane] : 0;
     };
-    fetch(0);
+    auto store_block = [&]() {                  // registers -> shared memory
+#pragma unroll
+        for (int k = 0; k < kDpBlk * kCMax / 32; ++k) bmp[lane + 32 * k] = r_mp[k];
+#pragma unroll
+        for (int k = 0; k < kDpBlk * kCMax / 64; ++k) s_bloc[w][lane + 32 * k] = r_loc[k];
+        bsr[lane] = r_sr;
+        if (lane < kDpBlk) bnc[lane] = static_cast<unsigned char>(r_nc);
+        __syncwarp();
+    };
+    load_block(0);
+    store_block();
+    load_block(1);
     for (int r = 0; r <= ut.R_last; ++r) {
         const int nfr = (r < ut.R_last) ? cf.F : ut.nl;
         const bool last_time = (r == ut.R_last);
         num_active += nfr;
         for (int i = 0; i < nfr; ++i) {
             const int g = r * cf.F + i;
-            const int ncand = n_nc;
-            const int loc = (lane < ncand) ? n_loc : -1;
-            const float mp = (lane < ncand) ? n_mp : 0.0f;
-            const float sta = n_sta, rr = n_rr;
-            fetch(g + 1);
+            const int fi = g & (kDpBlk - 1);
+            if (fi == 0 && g > 0) {
+                __syncwarp();                   // every lane is done with the previous block
+                store_block();
+                load_block((g >> 4) + 1);
+            }
+            const int ncand = bnc[fi];
+            const int loc = (lane < ncand) ? bloc[fi * kCMax + lane] : -1;
+            const float mp = (lane < ncand) ? bmp[fi * kCMax + lane] : 0.0f;
+            const float sta = bsr[fi], rr = bsr[kDpBlk + fi];
             const double lg = (loc > 0) ? s_log[loc] : 0.0;
             const float v_from_uv = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a / rr);
             const float uv_from_v = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr);
@@ -1299,7 +1332,8 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     if ((rc = ensure(ctx, ctx->ws.stat_map, (stat_tiles + 1) * sizeof(int)))) return rc;
     int *cand_map = static_cast<int *>(ctx->ws.cand_map.p), *stat_map = static_cast<int *>(ctx->ws.stat_map.p);
     const size_t per_fr = kCMax * (sizeof(short) + 2 * sizeof(float)) + 2 * sizeof(float) + 8;
-    if ((rc = ensure(ctx, ctx->ws.rapt_cand, (fr + 8) * per_fr))) return rc;
+    // (kDpBlk + frames of slack: the Viterbi pass loads whole 16-frame blocks, up to two past an utterance's end)
+    if ((rc = ensure(ctx, ctx->ws.rapt_cand, (fr + 48) * per_fr))) return rc;
 
     RaptParams p;
     memset(&p, 0, sizeof(p));
@@ -1317,7 +1351,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     p.total_ds = dsn;
     p.ds = static_cast<float *>(ctx->ws.rapt_ds.p);
     char *base = static_cast<char *>(ctx->ws.rapt_cand.p);
-    const long long frp = fr + 8;
+    const long long frp = fr + 48;
     p.mp = reinterpret_cast<float *>(base);
     p.f0c = p.mp + frp * kCMax;
     p.sta = p.f0c + frp * kCMax;

@@ -21,13 +21,16 @@
 //     of sm_100a (FADD2 / FMUL2 / FFMA2): the kernel is bound by instruction issue, not by HBM;
 //   * |A[k]|, |B[k]| of the two frames are stored interleaved so one 128-bit shared-memory load
 //     feeds two bins of both frames; the 941 non-zero mel weights are grouped in aligned runs of 4
-//     bins, bands are dealt to (slot, lane) by size so the loop is uniform across the warp.
+//     bins (302 groups); every lane walks a LIST of ~10 groups that strings several bands together
+//     (longest-processing-time assignment, then a local search that spreads the 8 lanes of each
+//     128-bit wavefront over the 8 bank groups), flushing its accumulator pair where a band ends.
 // Arithmetic is fp32 on the CUDA cores - no tensor cores (BASELINE.json north_star).
 #include "common.cuh"
 #include "tma.cuh"
 #include "fft_core.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace ssfe {
@@ -36,8 +39,8 @@ constexpr int kStftWarps = 12;
 constexpr int kStftThreads = kStftWarps * 32;
 constexpr int kPairFloats = kNfft + kHop;                   // 1280 samples = 5120 B per frame pair
 constexpr int kWarpTrans = 32 * kTransStride;               // float2 per warp
-constexpr int kMaxGroups = 24;
-constexpr int kMelSlots = 3;
+constexpr int kMaxGroups = 16;
+constexpr int kMelFlush = 1 << 15;                          // mel_k flag: the lane's band ends with this group
 
 struct PairInfo {            // 16 bytes, built on the device once per launch
     long long src;           // float offset of the pair's first sample in wavp
@@ -52,10 +55,8 @@ struct StftParams {
     float *out;
     const float *window;
     const float2 *tw;
-    const float4 *mel_w;     // [n_groups][32]
-    const int *mel_k;        // [n_groups][32] first bin of the group (multiple of 4)
-    const int *mel_band;     // [kMelSlots][32] band handled by (slot, lane), -1 = none
-    int slot_end[kMelSlots]; // cumulative group counts
+    const float4 *mel_w;     // [n_groups][32] weights of the lane's g-th group (already * 0.5)
+    const int *mel_k;        // [n_groups][32] swizzled address of the group | kMelFlush | band << 16
     int n_groups;
     float min_level, c1, c0;
 };
@@ -93,7 +94,7 @@ __global__ void stft_pairs_kernel(const int64_t *__restrict__ seg_off, const int
 struct __align__(16) WarpSmem {
     float stage[kPairFloats];            // 5120 B, TMA destination
     float2 trans[kWarpTrans];            // 8448 B; later re-used as the interleaved magnitudes
-    float outs[2 * kMels];               // 640 B
+    float2 outs[kMels];                  // 640 B: (frame A, frame B) mel sums of every band
     uint64_t bar;
     uint64_t pad;
 };
@@ -107,7 +108,6 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
     float *s_win = reinterpret_cast<float *>(s_tw + 1024);                 // [1024]
     float4 *s_mw = reinterpret_cast<float4 *>(s_win + 1024);               // [kMaxGroups][32]
     int *s_mk = reinterpret_cast<int *>(s_mw + kMaxGroups * 32);           // [kMaxGroups][32]
-    int *s_mb = s_mk + kMaxGroups * 32;                                    // [kMelSlots][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpSmem &ws = ws_all[warp];
@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
             s_mw[i] = p.mel_w[i];
             s_mk[i] = p.mel_k[i];
         }
-        for (int i = tid; i < kMelSlots * 32; i += kStftThreads) s_mb[i] = p.mel_band[i];
     }
     if (lane == 0) {
         mbar_init(&ws.bar, 1);
@@ -225,31 +224,33 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
         __syncwarp();
 
         if (MODE == 0) {
-            int g = 0;
-#pragma unroll
-            for (int s = 0; s < kMelSlots; ++s) {
-                float2 acc = make_float2(0.0f, 0.0f);
-                const int gend = p.slot_end[s];
-                for (; g < gend; ++g) {
-                    const int k0 = s_mk[g * 32 + lane];
-                    const float4 w = s_mw[g * 32 + lane];
-                    const float4 m01 = *reinterpret_cast<const float4 *>(mag2 + k0);          // swizzled first half
-                    const float4 m23 = *reinterpret_cast<const float4 *>(mag2 + (k0 ^ 2));
-                    acc = cfma_s(make_float2(m01.x, m01.y), w.x, acc);
-                    acc = cfma_s(make_float2(m01.z, m01.w), w.y, acc);
-                    acc = cfma_s(make_float2(m23.x, m23.y), w.z, acc);
-                    acc = cfma_s(make_float2(m23.z, m23.w), w.w, acc);
-                }
-                const int band = s_mb[s * 32 + lane];
-                if (band >= 0) {
-                    ws.outs[band] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, acc.x)), p.c0);
-                    ws.outs[kMels + band] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, acc.y)), p.c0);
+            float2 acc = make_float2(0.0f, 0.0f);
+            const int ng = p.n_groups;
+            for (int g = 0; g < ng; ++g) {
+                const int kw = s_mk[g * 32 + lane];
+                const float4 w = s_mw[g * 32 + lane];
+                const int k0 = kw & 0x3ff;
+                const float4 m01 = *reinterpret_cast<const float4 *>(mag2 + k0);          // swizzled first half
+                const float4 m23 = *reinterpret_cast<const float4 *>(mag2 + (k0 ^ 2));
+                acc = cfma_s(make_float2(m01.x, m01.y), w.x, acc);
+                acc = cfma_s(make_float2(m01.z, m01.w), w.y, acc);
+                acc = cfma_s(make_float2(m23.x, m23.y), w.z, acc);
+                acc = cfma_s(make_float2(m23.z, m23.w), w.w, acc);
+                if (kw & kMelFlush) {          // the band ends here: hand over its two sums, start the next band
+                    ws.outs[kw >> 16] = acc;
+                    acc = make_float2(0.0f, 0.0f);
                 }
             }
             __syncwarp();
+            // dB + normalise and store: frame A's 80 values, then frame B's
             float *dst = p.out + static_cast<long long>(cur.out_frame) * kMels;
             const int n_out = cur.has_b ? 2 * kMels : kMels;
-            for (int i = lane; i < n_out; i += 32) dst[i] = ws.outs[i];
+            const float *of = reinterpret_cast<const float *>(ws.outs);
+            for (int i = lane; i < n_out; i += 32) {
+                const int band = (i >= kMels) ? i - kMels : i;
+                const float m = of[2 * band + (i >= kMels ? 1 : 0)];
+                dst[i] = fmaf(p.c1, fast_log2(fmaxf(p.min_level, m)), p.c0);
+            }
         } else {
             float *dst = p.out + static_cast<long long>(cur.out_frame) * kBins;
             for (int i = lane; i < kBins; i += 32) dst[i] = 0.5f * mag2[i ^ ((i & 16) >> 3)].x;
@@ -261,8 +262,7 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
     }
 }
 
-constexpr size_t kStftSmem = kStftWarps * sizeof(WarpSmem) + 1024 * 8 + 1024 * 4 + kMaxGroups * 32 * (16 + 4) +
-                             kMelSlots * 32 * 4;
+constexpr size_t kStftSmem = kStftWarps * sizeof(WarpSmem) + 1024 * 8 + 1024 * 4 + kMaxGroups * 32 * (16 + 4);
 
 // ---- reflect padding into the segment layout (np.pad(x, 512, 'reflect'), utils.py:20) ---------
 __global__ void pad_reflect_kernel(const float *__restrict__ wav, const int64_t *__restrict__ off,
@@ -353,8 +353,6 @@ int stft_padded(ssfe_ctx *ctx, const float *wavp, const int64_t *seg_off_host, c
     p.tw = ctx->d_tw;
     p.mel_w = ctx->mel.w4;
     p.mel_k = ctx->mel.k0;
-    p.mel_band = ctx->mel.band;
-    for (int s = 0; s < kMelSlots; ++s) p.slot_end[s] = ctx->mel.slot_end[s];
     p.n_groups = ctx->mel.n_groups;
     p.min_level = static_cast<float>(ctx->cfg.min_level);
     p.c1 = static_cast<float>(0.2 * std::log10(2.0));
@@ -385,9 +383,12 @@ int init_stft_tables(ssfe_ctx *ctx)
     SSFE_CUDA(ctx, cudaMemcpy(ctx->d_window, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpy(ctx->d_tw, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
 
-    // mel: every band is a run of bins [kb, ke]; it is covered by aligned groups of 4 bins.  Bands are
-    // sorted by group count and dealt to (slot, lane): slot s of lane l handles band order[32 s + l], so
-    // the group loop of a slot has the same trip count for the whole warp (short bands get zero groups).
+    // mel: every band is a run of bins [kb, ke]; it is covered by aligned groups of 4 bins (302 groups for the
+    // reference basis).  Every lane gets a LIST of groups that strings several bands together: bands are dealt to
+    // the 32 lanes longest-first onto the least loaded lane (10 groups per lane instead of the 15 a
+    // one-band-per-(slot, lane) layout needed), then a local search reorders bands inside lanes and swaps them
+    // between lanes so that, at every step of the list, the 8 lanes that share a 128-bit shared-memory wavefront
+    // read from different bank groups (or the same address).
     const float *mb = ctx->mel_basis.data();   // [bin][band]
     int kb[kMels], ke[kMels], ng[kMels];
     for (int m = 0; m < kMels; ++m) {
@@ -403,61 +404,123 @@ int init_stft_tables(ssfe_ctx *ctx)
     std::vector<int> order(kMels);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ng[a] > ng[b]; });
-    static_assert(kMelSlots * 32 >= kMels, "not enough (slot, lane) cells for the bands");
-    int slot_groups[kMelSlots], total = 0;
-    for (int s = 0; s < kMelSlots; ++s) {
-        slot_groups[s] = 0;
-        for (int l = 0; l < 32 && s * 32 + l < kMels; ++l) slot_groups[s] = std::max(slot_groups[s], ng[order[s * 32 + l]]);
-        total += slot_groups[s];
-        ctx->mel.slot_end[s] = total;
+    // (the search below takes ~50 ms; a process creates several contexts - lanes, tests - with the same basis)
+    static std::vector<float> cache_basis;
+    static std::vector<std::vector<int>> cache_lists;
+    static int cache_cost = 0;
+    const bool cached = cache_basis == ctx->mel_basis;
+    std::vector<std::vector<int>> lists(32);
+    int load[32] = {};
+    if (cached) {
+        lists = cache_lists;
+        for (int l = 0; l < 32; ++l)
+            for (int m : lists[l]) load[l] += ng[m];
+    } else {
+        for (int m : order) {
+            if (ng[m] == 0) continue;
+            int l = 0;
+            for (int i = 1; i < 32; ++i)
+                if (load[i] < load[l]) l = i;
+            lists[l].push_back(m);
+            load[l] += ng[m];
+        }
     }
+    int total = *std::max_element(load, load + 32);
     if (total > kMaxGroups || total == 0)
         return set_error(ctx, SSFE_ERR_INVALID, "mel basis too dense for the fused kernel (%d groups per lane)", total);
-    std::vector<float4> w4(static_cast<size_t>(total) * 32, make_float4(0.f, 0.f, 0.f, 0.f));
-    std::vector<int> k0(static_cast<size_t>(total) * 32, 0), band(kMelSlots * 32, -1);
-    int gbase = 0;
-    for (int s = 0; s < kMelSlots; ++s) {
-        // place the slot's bands on lanes so that the 8 lanes of a quarter warp (one 128-bit shared
-        // memory wavefront) start in different 16-byte bank groups: first group index distinct mod 8
-        int lane_band[32];
-        bool used[4][8] = {};
-        int fill[4] = {0, 0, 0, 0};
-        for (int l = 0; l < 32; ++l) lane_band[l] = -1;
-        std::vector<int> leftover;
-        for (int l = 0; l < 32 && s * 32 + l < kMels; ++l) {
-            const int m = order[s * 32 + l];
-            const int res = (kb[m] >> 2) & 7;
-            int q = -1;
-            for (int c = 0; c < 4; ++c)
-                if (!used[c][res] && fill[c] < 8 && (q < 0 || fill[c] < fill[q])) q = c;
-            if (q < 0) { leftover.push_back(m); continue; }
-            used[q][res] = true;
-            lane_band[q * 8 + fill[q]++] = m;
+    // bank group (16-byte unit mod 8) of the first half of group q = k / 4 in the swizzled magnitude array; the
+    // second half sits in the neighbouring unit (^ 1), so both halves see the same conflicts
+    auto bank_of = [](int q) { return 2 * (q & 3) + ((q >> 2) & 1); };
+    auto lane_groups = [&](int l, int *qs) {          // group index of every step of lane l, -1 = padding
+        int n = 0;
+        for (int m : lists[l])
+            for (int g = 0; g < ng[m]; ++g) qs[n++] = (kb[m] >> 2) + g;
+        for (; n < total; ++n) qs[n] = -1;
+    };
+    auto cost = [&]() {
+        int qs[32][kMaxGroups], c = 0;
+        for (int l = 0; l < 32; ++l) lane_groups(l, qs[l]);
+        for (int st = 0; st < total; ++st)
+            for (int qw = 0; qw < 4; ++qw) {
+                int worst = 1;
+                for (int b = 0; b < 8; ++b) {
+                    int distinct = 0, seen[8];
+                    for (int l = 8 * qw; l < 8 * qw + 8; ++l) {
+                        const int q = qs[l][st] < 0 ? 0 : qs[l][st];     // padding reads group 0
+                        if (bank_of(q) != b) continue;
+                        bool dup = false;
+                        for (int i = 0; i < distinct; ++i) dup = dup || seen[i] == q;
+                        if (!dup) seen[distinct++] = q;
+                    }
+                    worst = std::max(worst, distinct);
+                }
+                c += worst;
+            }
+        return c;
+    };
+    if (cached) {
+        ctx->mel.conflict_cost = cache_cost;
+    } else {
+        uint32_t rng = 12345u;
+        auto rnd = [&](int n) { rng = rng * 1664525u + 1013904223u; return static_cast<int>((rng >> 8) % static_cast<uint32_t>(n)); };
+        int best = cost();
+        for (int it = 0; it < 20000 && best > 4 * total; ++it) {
+            const int a = rnd(32), b2 = rnd(32);
+            const int kind = rnd(3);
+            if (kind == 0) {                                  // swap two whole lanes (changes the quarter-warp mix)
+                std::swap(lists[a], lists[b2]);
+                std::swap(load[a], load[b2]);
+                const int c = cost();
+                if (c <= best) best = c;
+                else { std::swap(lists[a], lists[b2]); std::swap(load[a], load[b2]); }
+            } else if (kind == 1) {                           // reorder the bands inside a lane
+                if (lists[a].size() < 2) continue;
+                const int i = rnd(static_cast<int>(lists[a].size())), j = rnd(static_cast<int>(lists[a].size()));
+                std::swap(lists[a][i], lists[a][j]);
+                const int c = cost();
+                if (c <= best) best = c;
+                else std::swap(lists[a][i], lists[a][j]);
+            } else {                                          // exchange one band between two lanes
+                if (a == b2 || lists[a].empty() || lists[b2].empty()) continue;
+                const int i = rnd(static_cast<int>(lists[a].size())), j = rnd(static_cast<int>(lists[b2].size()));
+                const int la = load[a] - ng[lists[a][i]] + ng[lists[b2][j]], lb = load[b2] - ng[lists[b2][j]] + ng[lists[a][i]];
+                if (la > total || lb > total) continue;
+                std::swap(lists[a][i], lists[b2][j]);
+                const int c = cost();
+                if (c <= best) { best = c; load[a] = la; load[b2] = lb; }
+                else std::swap(lists[a][i], lists[b2][j]);
+            }
         }
-        for (int m : leftover)
-            for (int l = 0; l < 32; ++l)
-                if (lane_band[l] < 0) { lane_band[l] = m; break; }
-        for (int l = 0; l < 32; ++l) {
-            const int m = lane_band[l];
-            if (m < 0) continue;
-            band[s * 32 + l] = m;
-            for (int g = 0; g < ng[m]; ++g) {
+        ctx->mel.conflict_cost = best;
+        if (getenv("SSFE_TRACE_HOST"))
+            fprintf(stderr, "[stft] mel layout: %d groups per lane, %d wavefronts per half-load pass (ideal %d)\n", total, best, 4 * total);
+        cache_basis = ctx->mel_basis;
+        cache_lists = lists;
+        cache_cost = best;
+    }
+    std::vector<float4> w4(static_cast<size_t>(total) * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> k0(static_cast<size_t>(total) * 32, 0);
+    for (int l = 0; l < 32; ++l) {
+        int st = 0;
+        for (int m : lists[l])
+            for (int g = 0; g < ng[m]; ++g, ++st) {
                 const int k = (kb[m] & ~3) + 4 * g;
                 float wv[4];
                 for (int q = 0; q < 4; ++q) wv[q] = (k + q < kBins) ? 0.5f * mb[(k + q) * kMels + m] : 0.0f;   // 1/2 of the frame split, exact
-                w4[(gbase + g) * 32 + l] = make_float4(wv[0], wv[1], wv[2], wv[3]);
-                k0[(gbase + g) * 32 + l] = k ^ ((k & 16) >> 3);      // swizzled address of the first half
+                w4[st * 32 + l] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+                int kw = k ^ ((k & 16) >> 3);                  // swizzled address of the first half
+                if (g == ng[m] - 1) kw |= kMelFlush | (m << 16);
+                k0[st * 32 + l] = kw;
             }
-        }
-        gbase += slot_groups[s];
     }
+    // a band without any non-zero weight never gets flushed: its output is 0.84 + 0.2 log10(min_level) like the reference's
+    for (int m = 0; m < kMels; ++m)
+        if (ng[m] == 0) return set_error(ctx, SSFE_ERR_INVALID, "mel band %d of the basis is empty", m);
     ctx->mel.n_groups = total;
     SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.w4, w4.size() * sizeof(float4)));
     SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.k0, k0.size() * sizeof(int)));
-    SSFE_CUDA(ctx, cudaMalloc(&ctx->mel.band, band.size() * sizeof(int)));
     SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.w4, w4.data(), w4.size() * sizeof(float4), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.k0, k0.data(), k0.size() * sizeof(int), cudaMemcpyHostToDevice));
-    SSFE_CUDA(ctx, cudaMemcpy(ctx->mel.band, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
     SSFE_CUDA(ctx, cudaFuncSetAttribute(stft_mel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kStftSmem)));
     SSFE_CUDA(ctx, cudaFuncSetAttribute(stft_mel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -471,12 +534,10 @@ void free_stft_tables(ssfe_ctx *ctx)
     cudaFree(ctx->d_tw);
     cudaFree(ctx->mel.w4);
     cudaFree(ctx->mel.k0);
-    cudaFree(ctx->mel.band);
     ctx->d_window = nullptr;
     ctx->d_tw = nullptr;
     ctx->mel.w4 = nullptr;
     ctx->mel.k0 = nullptr;
-    ctx->mel.band = nullptr;
 }
 
 }  // namespace ssfe
