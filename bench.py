@@ -488,6 +488,62 @@ def leg_collate(fe, dev, mine, fr, outs, cpu=True, n_steps=200):
     return res
 
 
+def leg_script(fe, dev, n_speakers=109, utts=40):
+    """the script form end to end - a WAV tree (109 speakers x 40 files) + spk2gen.pkl in,
+    the spmel / raptf0 NPY trees out (make_spect_f0.py:19-74) - and where its wall time goes."""
+    import pickle
+    import shutil
+    import wave
+
+    from speechsplit_b200 import make_spect_f0 as msf
+    from speechsplit_b200.corpus import control_tracks, make_manifest
+    metas = make_manifest(n_speakers, utts, seed=7)
+    tracks = get_pool().map(control_tracks, metas, chunksize=64)
+    x, off = synth_on_gpu(metas, tracks, dev)
+    pcm = x.cpu().numpy()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="ssfe_script_", dir=base)
+    try:
+        spk2gen = {}
+        for i, m in enumerate(metas):
+            d = os.path.join(tmp, "wavs", m.spk)
+            os.makedirs(d, exist_ok=True)
+            spk2gen[m.spk] = m.gender
+            with wave.open(os.path.join(d, "%s_%03d.wav" % (m.spk, m.index + 1)), "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(FS)
+                w.writeframes(pcm[off[i]:off[i + 1]].tobytes())
+        with open(os.path.join(tmp, "spk2gen.pkl"), "wb") as fh:
+            pickle.dump(spk2gen, fh)
+
+        def run(tag):
+            st = {}
+            t0 = time.perf_counter()
+            msf.make_spect_f0(os.path.join(tmp, "wavs"), os.path.join(tmp, "spmel" + tag), os.path.join(tmp, "raptf0" + tag),
+                              os.path.join(tmp, "spk2gen.pkl"), device=dev.index, verbose=False, stats=st)
+            st["wall_s"] = time.perf_counter() - t0
+            return st
+
+        run("_warm")
+        st = run("")
+        n_files = int(st.get("files", 0))
+        audio_s = float(off[-1]) / FS
+        # one file back through numpy, as data_loader.py:62-63 reads it
+        m0 = metas[0]
+        a = np.load(os.path.join(tmp, "spmel", m0.spk, "%s_%03d.npy" % (m0.spk, 1)))
+        ok = bool(a.dtype == np.float32 and a.ndim == 2 and a.shape[1] == 80)
+        return {"workload": "script form: %d speakers x %d WAV files (16-bit PCM, %.0f audio-s) -> spmel/ + raptf0/ NPY trees, files on %s"
+                            % (n_speakers, utts, audio_s, "tmpfs" if base else "disk"),
+                "files": n_files, "files_per_s": n_files / st["wall_s"], "audio_s_per_s": audio_s / st["wall_s"],
+                "wall_s": st["wall_s"], "read_wav_s": st.get("read_s"), "pack_s": st.get("pack_s"),
+                "gpu_extract_host_s": st.get("extract_s"), "write_npy_s": st.get("write_s"), "extract_calls": st.get("calls"),
+                "other_python_s": st["wall_s"] - sum(st.get(k, 0.0) for k in ("read_s", "pack_s", "extract_s", "write_s")),
+                "npy_readback_ok": ok}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ---- our arm --------------------------------------------------------------------------------------
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -686,7 +742,8 @@ def run_ours(args):
         configs = {}
         for name, fn in (("single", lambda: leg_single(fe, dev)),
                          ("collate", lambda: leg_collate(fe, dev, mine, fr, outs, cpu=not args.no_cpu_baseline)),
-                         ("longform", lambda: leg_longform(fe, dev))):
+                         ("longform", lambda: leg_longform(fe, dev)),
+                         ("script", lambda: leg_script(fe, dev))):
             try:
                 configs[name] = fn()
             except Exception as ex:           # a failed side leg must not take the bench line with it
