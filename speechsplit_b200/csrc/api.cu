@@ -461,7 +461,8 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     mark(ctx, ST_FILTFILT);
     int64_t *d_seg = upload(ctx, seg.data(), n + 1);
     int64_t *d_fix = upload(ctx, fix.data(), n + 1);
-    if (!d_seg || !d_fix) return SSFE_ERR_NOMEM;
+    int64_t *d_foff = upload(ctx, foff.data(), n + 1);          // for the F0 post-processing at the end of the call
+    if (!d_seg || !d_fix || !d_foff) return SSFE_ERR_NOMEM;
     FiltOut fo;
     fo.dith = dith;
     fo.wavp = wavp;
@@ -485,7 +486,7 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
     }
     if ((rc = rapt_run(ctx, wavp, start.data(), len.data(), foff.data(), n, b->f0_lo, b->f0_hi, f0_raw))) return rc;
     mark(ctx, ST_POST);
-    rc = f0_post_run(ctx, f0_raw, foff.data(), n, o->f0_norm, nullptr, o->onehot, o->bins);
+    rc = f0_post_run(ctx, f0_raw, foff.data(), n, o->f0_norm, nullptr, o->onehot, o->bins, d_foff);
     mark(ctx, ST_COUNT);
     return rc;
 }

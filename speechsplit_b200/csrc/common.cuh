@@ -63,8 +63,8 @@ struct ssfe_ctx {
     int aux_idx = 0;
     bool mt_attr_set = false;
     // MT19937 jump-ahead tap lists (mt19937.cu): slot + 1 per (level, digit), 0 = not built yet
-    int mt_slot[5][3][256] = {};                              // [log2(segment blocks) - 8][level][digit]
-    int mt_cnt[5][3][256] = {};
+    int mt_slot[8][3][256] = {};                              // [log2(segment blocks) - 5][level][digit]
+    int mt_cnt[8][3][256] = {};
     uint16_t *mt_taps = nullptr;
     int mt_slots_used = 0, mt_slots_cap = 0;
     ssfe_config cfg;
@@ -211,6 +211,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host /* 
 
 // a7+a8 (+a9 when bins/onehot given) over a ragged batch; frame offsets are HOST [n+1]
 int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_host, int n,
-                float *f0_norm_dev, float *stats_dev, float *onehot, int64_t *bins);
+                float *f0_norm_dev, float *stats_dev, float *onehot, int64_t *bins,
+                const int64_t *frame_off_dev = nullptr);
 
 }  // namespace ssfe

@@ -224,7 +224,7 @@ static int64_t grid_for(int64_t work, int threads) { return (work + threads - 1)
 
 namespace ssfe {
 int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_host, int n, float *f0_norm_dev,
-                float *stats_dev, float *onehot, int64_t *bins)
+                float *stats_dev, float *onehot, int64_t *bins, const int64_t *frame_off_dev)
 {
     const int64_t total = frame_off_host[n];
     if (n == 0 || total == 0) return SSFE_OK;
@@ -235,9 +235,12 @@ int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_hos
     float *stats = stats_dev ? stats_dev : scratch + total;
     int64_t *tmp_bins = reinterpret_cast<int64_t *>(
         reinterpret_cast<char *>(ctx->ws.misc.p) + (total * sizeof(float) + static_cast<size_t>(n) * 2 * sizeof(float) + 7) / 8 * 8);
-    int64_t *d_off = upload(ctx, frame_off_host, n + 1);
-    if (!d_off) return SSFE_ERR_NOMEM;
-    if ((rc = flush_meta(ctx))) return rc;
+    const int64_t *d_off = frame_off_dev;       // ssfe_extract uploaded it with the first stage's metadata
+    if (!d_off) {
+        d_off = upload(ctx, frame_off_host, n + 1);
+        if (!d_off) return SSFE_ERR_NOMEM;
+        if ((rc = flush_meta(ctx))) return rc;
+    }
     f0_stats_kernel<<<static_cast<unsigned>(grid_for(n, 64)), 64, 0, ctx->stream>>>(f0_dev, d_off, n, scratch, stats);
     SSFE_LAUNCHED(ctx);
     int64_t *use_bins = bins ? bins : (onehot ? tmp_bins : nullptr);

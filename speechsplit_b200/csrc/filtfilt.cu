@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
 constexpr int kTileW = 32;                   // samples per row and sub-step
 constexpr int kTileStride = kTileW + 1;      // doubles per tile row (column reads are conflict-free)
 constexpr int kFiltWarps = 4;
+#ifndef SSFE_FILT_BWD_CTAS
+#define SSFE_FILT_BWD_CTAS 4      // CTAs per SM the backward final pass is compiled for (5 spills 120 bytes; A/B in profiles/)
+#endif
 
 // The cascade the scan runs (see the file header): 13 fp64 operations per sample, FMAs allowed.
 struct Casc {
@@ -213,7 +216,7 @@ template <> struct RawType<SSFE_I16, 0> { using T = short; };
 template <> struct RawType<SSFE_F64, 0> { using T = double; };
 
 template <int DTYPE, int PASS, bool FINAL>
-__global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
+__global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : SSFE_FILT_BWD_CTAS)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
                                                                      int n_tiles, const int *__restrict__ tile_map)
 {
     __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
@@ -445,60 +448,84 @@ __global__ void __launch_bounds__(kFiltWarps * 32, (PASS == 0 ? 5 : 4)) filt_til
 // ---- carry ---------------------------------------------------------------------------------------------
 // Turn the zero-state finals into true chunk-entry states: z' = M z + s per chunk, M = A_c^256 of the cascade.
 // Its entries are O(10) and the recurrence is well conditioned, so this is plain fp64 (the DF2T realisation
-// needed double-double here, five lanes per utterance and a warp-wide scan for long utterances).  One thread
-// per utterance; the zero-state final of the next chunk is fetched while this chunk's update is computed.
-// A 3 s utterance is 188 steps of a five-deep FMA chain (~6 us), a 60 s one 3 751 (~0.12 ms).
-constexpr int kCarryThreads = 64;
+// needed double-double here, five lanes per utterance and a warp-wide scan for long utterances).
+// A QUARTER-WARP per utterance: the zero-state finals of 8 chunks are fetched by its 8 lanes at once (and the next
+// 8 while these are consumed), staged in shared memory, and every lane walks the 8 dependent steps redundantly - a
+// five-deep FMA chain each, no shuffles; lane i keeps the state it sees at step i, so the entry states leave with
+// one store round per tile.  (One thread per utterance with a one-step prefetch paid a trip to L2 per chunk: 65 us
+// per pass for a single 3 s utterance and 1.3 ms for a batch of 60 s ones; a whole warp per utterance did the work
+// 32 times over and cost the full corpus 0.3 ms per pass.  This takes ~7 us for one utterance, 0.1 ms for 3 751
+// chunks, and the full corpus as long as the one-thread version.)  Control flow is uniform across the warp's four
+// utterances: the tile loop runs to the longest of them, everything else is predicated.
+constexpr int kCarryWarps = 4, kCarrySub = 4, kCarryTile = 8;
 
 template <int DTYPE, int PASS>
-__global__ void __launch_bounds__(kCarryThreads) filt_carry_kernel(const FiltParams p)
+__global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_kernel(const FiltParams p)
 {
-    const int u = blockIdx.x * kCarryThreads + threadIdx.x;
-    if (u >= p.n) return;
-    const int c0 = p.chunk_off[u], nc = p.chunk_off[u + 1] - c0;
-    const int64_t L = p.in_off[u + 1] - p.in_off[u];
-    const int64_t fbase = p.fix_off[u];
-    const int64_t Lf = p.fix_off[u + 1] - fbase;
-    const int64_t M = Lf + 2 * kPadLen;
-    const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
-    double x0;
-    if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
-    else x0 = static_cast<double>(p.y1f[ebase + M - 1]);
-    double z[5], nx[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        z[i] = c_filt.zic[i] * x0;                       // scipy's zi * x[0], in cascade coordinates
-        nx[i] = 0.0;
+    __shared__ double s_fin[kCarryWarps][kCarrySub * kCarryTile * 5];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane >> 3, l8 = lane & 7;
+    const int u = (blockIdx.x * kCarryWarps + w) * kCarrySub + sub;
+    const bool live = u < p.n;
+    int c0 = 0, nc = 0;
+    double x0 = 0.0;
+    if (live) {
+        c0 = p.chunk_off[u];
+        nc = p.chunk_off[u + 1] - c0;
+        const int64_t L = p.in_off[u + 1] - p.in_off[u];
+        const int64_t fbase = p.fix_off[u];
+        const int64_t Lf = p.fix_off[u + 1] - fbase;
+        const int64_t M = Lf + 2 * kPadLen;
+        const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
+        if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
+        else x0 = static_cast<double>(p.y1f[ebase + M - 1]);
     }
+    const int nmax = __reduce_max_sync(0xffffffffu, nc);
+    double z[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) z[i] = c_filt.zic[i] * x0;       // scipy's zi * x[0], in cascade coordinates
     const double *__restrict__ s_in = p.state + static_cast<int64_t>(c0) * 5;
     double *__restrict__ zout = p.zin + static_cast<int64_t>(c0) * 5;
-    if (nc > 1) {
+    double *fin = s_fin[w] + sub * (kCarryTile * 5);
+    double pre[5];
+    auto load_tile = [&](int t0) {                                // finals of chunks t0 .. t0 + 7 (the last chunk has none)
 #pragma unroll
-        for (int i = 0; i < 5; ++i) nx[i] = s_in[i];
-    }
-    for (int c = 0; c < nc; ++c) {
-        double sc[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            sc[i] = nx[i];
-            zout[c * 5 + i] = z[i];                      // z_in of this chunk
+        for (int k = 0; k < 5; ++k) {
+            const int idx = l8 + kCarryTile * k, ch = t0 + idx / 5;
+            pre[k] = (ch + 1 < nc) ? s_in[static_cast<int64_t>(t0) * 5 + idx] : 0.0;
         }
-        if (c + 2 < nc) {                                // (the last chunk has no zero-state final)
+    };
+    load_tile(0);
+    for (int t0 = 0; t0 < nmax; t0 += kCarryTile) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) nx[i] = s_in[(c + 1) * 5 + i];
-        }
-        if (c + 1 < nc) {
-            double t[5];
+        for (int k = 0; k < 5; ++k) fin[l8 + kCarryTile * k] = pre[k];
+        __syncwarp();
+        load_tile(t0 + kCarryTile);                               // in flight during the steps below (predicated by nc)
+        const int cnt = nc - t0;                                  // chunks of this utterance in the tile (may be <= 0)
+        double keep[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                double acc = sc[i];
+        for (int i = 0; i < kCarryTile; ++i) {
+            if (l8 == i) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) acc = fma(c_filt.mc[i * 5 + k], z[k], acc);
-                t[i] = acc;
+                for (int k = 0; k < 5; ++k) keep[k] = z[k];       // z_in of chunk t0 + i
             }
+            if (i + 1 < cnt) {
+                double t[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) z[i] = t[i];
+                for (int r = 0; r < 5; ++r) {
+                    double acc = fin[i * 5 + r];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) acc = fma(c_filt.mc[r * 5 + k], z[k], acc);
+                    t[r] = acc;
+                }
+#pragma unroll
+                for (int r = 0; r < 5; ++r) z[r] = t[r];
+            }
         }
+        if (l8 < cnt) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) zout[static_cast<int64_t>(t0 + l8) * 5 + k] = keep[k];
+        }
+        __syncwarp();                                             // fin is rewritten by the next tile
     }
 }
 
@@ -535,7 +562,7 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
-    const unsigned gu = (p.n + kCarryThreads - 1) / kCarryThreads;
+    const unsigned gu = (p.n + kCarryWarps * kCarrySub - 1) / (kCarryWarps * kCarrySub);
     cudaStream_t st = ctx->stream;
     if (sequential) {
         filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
@@ -549,14 +576,14 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     }
     filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
-    filt_carry_kernel<DTYPE, 0><<<gu, kCarryThreads, 0, st>>>(p);
+    filt_carry_kernel<DTYPE, 0><<<gu, kCarryWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     p.y1f = p.y1f_out;
     filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
-    filt_carry_kernel<DTYPE, 1><<<gu, kCarryThreads, 0, st>>>(p);
+    filt_carry_kernel<DTYPE, 1><<<gu, kCarryWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
     filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
