@@ -1017,25 +1017,36 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
             const float uv_from_v = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr);
             float errmin = FLT_MAX;
             int minloc = 0;
-            // only the previous frame's live candidates are visited (typically 3-5 of the 20 slots;
-            // the count is warp-uniform, so the shuffles sit inside the loop)
-#pragma unroll 2
-            for (int j = 0; j < ncandp; ++j) {
-                const int loc1 = __shfl_sync(full_mask, loc_prev, j);
-                const float dp = __shfl_sync(full_mask, d_prev, j);
-                const double lg1 = __shfl_sync(full_mask, lg_prev, j);
-                {
-                    float ferr;
-                    if (loc > 0) {
-                        if (loc1 > 0) {
-                            if (use_log) ferr = jump_cost(static_cast<float>(lg - lg1), c_rapt.ln2, c_rapt.fdouble, c_rapt.freqwt);
-                            else ferr = ferr_tab[(loc1 - cf.start) * cf.nlags + (loc - cf.start)];
-                        } else {
-                            ferr = v_from_uv;
-                        }
-                    } else {
-                        ferr = (loc1 > 0) ? uv_from_v : 0.0f;
+            // Only the previous frame's live candidates are visited (typically 3-5 of the 20 slots; the count is
+            // warp-uniform).  They are taken four at a time, branch-free: the twelve shuffles of a group go out
+            // together and the four costs are formed side by side - one frame is one dependent chain, and with a
+            // candidate per iteration and divergent branches around the cost it was ~290 instructions long.
+            if (use_log) {
+                const bool v_cur = loc > 0;
+                for (int j0 = 0; j0 < ncandp; j0 += 4) {
+                    float errs[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j0 + jj;
+                        const int loc1 = __shfl_sync(full_mask, loc_prev, j);
+                        const float dp = __shfl_sync(full_mask, d_prev, j);
+                        const double lg1 = __shfl_sync(full_mask, lg_prev, j);
+                        const float jc = jump_cost(static_cast<float>(lg - lg1), c_rapt.ln2, c_rapt.fdouble, c_rapt.freqwt);
+                        const bool v_prev = loc1 > 0;
+                        const float ferr = v_cur ? (v_prev ? jc : v_from_uv) : (v_prev ? uv_from_v : 0.0f);
+                        errs[jj] = (j < ncandp) ? ferr + dp : FLT_MAX;
                     }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)                 // first minimum wins, in candidate order
+                        if (errs[jj] < errmin) { errmin = errs[jj]; minloc = j0 + jj; }
+                }
+            } else {
+                for (int j = 0; j < ncandp; ++j) {
+                    const int loc1 = __shfl_sync(full_mask, loc_prev, j);
+                    const float dp = __shfl_sync(full_mask, d_prev, j);
+                    float ferr;
+                    if (loc > 0) ferr = (loc1 > 0) ? ferr_tab[(loc1 - cf.start) * cf.nlags + (loc - cf.start)] : v_from_uv;
+                    else ferr = (loc1 > 0) ? uv_from_v : 0.0f;
                     const float err = ferr + dp;
                     if (err < errmin) { errmin = err; minloc = j; }
                 }
