@@ -536,12 +536,15 @@ static int extract_host_pipeline(ssfe_ctx *ctx, const ssfe_batch *b, const void 
     // Sub-batches of ~kChunkSamples, cut preferably where the speaker changes.  The first upload and the
     // last download are not hidden behind anything, so the schedule ramps up (1/4, 1/2, 1, 1, ...) and
     // down again (..., 1/2, 1/4).
-    // full-size sub-batch: an eighth of the call, between 16 M and 256 M samples.  (A constant 256 M cut the
-    // 262 M-sample share of one GPU of eight into 32 / 32 / 134 / 64 M - no pipeline to speak of.)  The test hook
-    // SSFE_HOST_CHUNK_SAMPLES overrides it.
+    // full-size sub-batch: a sixteenth of the call, between 32 M and 128 M samples.  Measured on the full corpus
+    // (2.09 G samples; e2e relative to the box's bare-copy time in the same run): 256 M 1.07, 192 M ... 32 M 1.02 -
+    // the kernels of a sub-batch finish one sub-batch time after its upload, so the tail after the LAST upload
+    // shrinks with the sub-batch; on one GPU's share of eight (262 M samples) 32 M sub-batches took 15.6 ms, 16 M
+    // 16.1, 8 M 19.3 (their fixed latencies add up).  (Round 1's constant 256 M cut that share into 32 / 32 / 134 /
+    // 64 M - no pipeline to speak of.)  The test hook SSFE_HOST_CHUNK_SAMPLES overrides it.
     const int64_t total_samples = b->sample_offsets[n] - b->sample_offsets[0];
     const int64_t kChunkSamples = ctx->host_chunk_forced ? ctx->host_chunk_samples
-                                                         : std::min<int64_t>(std::max<int64_t>(total_samples / 8, 16LL << 20), 256LL << 20);
+                                                         : std::min<int64_t>(std::max<int64_t>(total_samples / 16, 32LL << 20), 128LL << 20);
     std::vector<int64_t> targets;
     {
         // ramp up (T/8, T/8, T/4, T/4, T/2, T/2), full sub-batches, ramp down (T/2, T/4, T/8, T/16): nothing hides
