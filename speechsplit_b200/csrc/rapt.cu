@@ -556,35 +556,26 @@ __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const Rap
         float wv[7], dot[7], s2 = 0.0f;
 #pragma unroll
         for (int k = 0; k < 7; ++k) { wv[k] = xs[k]; dot[k] = 0.0f; }
-        // 120 steps; at step j the registers hold x[st + j .. st + j + 6] (wv[(j + t) % 7] = x[st + j + t])
+        // 120 steps; at step j the registers hold x[st + j .. st + j + 6] (wv[(j + t) % 7] = x[st + j + t]).  The
+        // body is unrolled by exactly one rotation of the window (7 steps, ~120 instructions): a 28-step body with
+        // 128-bit reference reads was 4 % fewer instructions but, in a 67 KB kernel, cost instruction-cache misses
+        // (ncu: `no_inst` was the top stall of these lines).
 #pragma unroll 1
-        for (int jb = 0; jb < 112; jb += 28) {
+        for (int jb = 0; jb < 119; jb += 7) {
 #pragma unroll
-            for (int jj = 0; jj < 28; jj += 4) {
-                const float4 r4 = *reinterpret_cast<const float4 *>(xr + jb + jj);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float r = (q == 0) ? r4.x : (q == 1) ? r4.y : (q == 2) ? r4.z : r4.w;
-                    const int ph = (jj + q) % 7;
-#pragma unroll
-                    for (int t = 0; t < 7; ++t) dot[t] += r * wv[(ph + t) % 7];
-                    s2 += wv[ph] * wv[ph];
-                    wv[ph] = xs[jb + jj + q + 7];
-                }
-            }
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; jj += 4) {             // steps 112 .. 119 (112 = 0 mod 7)
-            const float4 r4 = *reinterpret_cast<const float4 *>(xr + 112 + jj);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float r = (q == 0) ? r4.x : (q == 1) ? r4.y : (q == 2) ? r4.z : r4.w;
-                const int ph = (jj + q) % 7;
+            for (int ph = 0; ph < 7; ++ph) {
+                const float r = xr[jb + ph];
 #pragma unroll
                 for (int t = 0; t < 7; ++t) dot[t] += r * wv[(ph + t) % 7];
                 s2 += wv[ph] * wv[ph];
-                wv[ph] = xs[112 + jj + q + 7];
+                wv[ph] = xs[jb + ph + 7];
             }
+        }
+        {                                               // step 119 (119 = 0 mod 7)
+            const float r = xr[119];
+#pragma unroll
+            for (int t = 0; t < 7; ++t) dot[t] += r * wv[t % 7];
+            s2 += wv[0] * wv[0];
         }
         // reference energy of my frame: from the lane that holds its reference item
         const float engr = __shfl_sync(0xffffffffu, s2, base_f + st_n[my_f]);
