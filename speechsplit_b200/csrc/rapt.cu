@@ -553,29 +553,50 @@ __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const Rap
         }
         const float *xr = xf + my_f * kXfStride;       // reference window of my frame
         const float *xs = xr + my_st;                  // my candidate's first lagged window
-        float wv[7], dot[7], s2 = 0.0f;
+        // The chains are SKEWED so that they share their multiplicand: chain t (lag st + t) takes its j-th term at
+        // time tau = j + t, and at time tau every chain multiplies the same sample x[st + tau] - the one value the lane
+        // loads per step - by ref[tau - t]:   dot_t = sum_tau ref[tau - t] * x[st + tau],  tau = 0 .. 125, ref = 0
+        // outside 0 .. 119 (a term 0 * x adds exactly nothing, and every chain still sums its own products in
+        // ascending j, product rounded before the add).  The reference values are the same for all lanes of a frame
+        // (broadcast reads), so the chains advance as PACKED pairs (t, t + 1) against (ref[tau - t], ref[tau - t - 1])
+        // - FMUL2 + FFMA2 with the hidden 1.0 (p2add) - without any per-lane repacking: three packed pairs, chain 6
+        // and the window energy (x^2, tau < 120) scalar.  14 instead of 18 instructions per step; the body is one
+        // rotation of the six-deep ring of reference pairs.
+        float dot[7], s2 = 0.0f;
+        {
+            p2 a01 = p2pack(0.0f, 0.0f), a23 = a01, a45 = a01;
+            float a6 = 0.0f;
+            p2 q[6];                                          // q[(tau - k) % 6] = (ref[tau - k], ref[tau - k - 1])
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { wv[k] = xs[k]; dot[k] = 0.0f; }
-        // 120 steps; at step j the registers hold x[st + j .. st + j + 6] (wv[(j + t) % 7] = x[st + j + t]).  The
-        // body is unrolled by exactly one rotation of the window (7 steps, ~120 instructions): a 28-step body with
-        // 128-bit reference reads was 4 % fewer instructions but, in a 67 KB kernel, cost instruction-cache misses
-        // (ncu: `no_inst` was the top stall of these lines).
+            for (int k = 0; k < 6; ++k) q[k] = a01;
 #pragma unroll 1
-        for (int jb = 0; jb < 119; jb += 7) {
+            for (int tb = 0; tb < 120; tb += 6) {
 #pragma unroll
-            for (int ph = 0; ph < 7; ++ph) {
-                const float r = xr[jb + ph];
-#pragma unroll
-                for (int t = 0; t < 7; ++t) dot[t] += r * wv[(ph + t) % 7];
-                s2 += wv[ph] * wv[ph];
-                wv[ph] = xs[jb + ph + 7];
+                for (int ph = 0; ph < 6; ++ph) {
+                    const int tau = tb + ph;
+                    const float x1 = xs[tau];
+                    q[ph] = p2pack(xr[tau], (tau > 0) ? xr[tau - 1] : 0.0f);
+                    const p2 xx = p2pack(x1, x1);
+                    a01 = p2add(a01, p2mul(xx, q[ph]));
+                    a23 = p2add(a23, p2mul(xx, q[(ph + 4) % 6]));          // (ref[tau - 2], ref[tau - 3])
+                    a45 = p2add(a45, p2mul(xx, q[(ph + 2) % 6]));          // (ref[tau - 4], ref[tau - 5])
+                    a6 += x1 * p2hi(q[(ph + 1) % 6]);                      // ref[tau - 6] = second half of the pair of tau - 5
+                    s2 += x1 * x1;
+                }
             }
-        }
-        {                                               // step 119 (119 = 0 mod 7)
-            const float r = xr[119];
 #pragma unroll
-            for (int t = 0; t < 7; ++t) dot[t] += r * wv[t % 7];
-            s2 += wv[0] * wv[0];
+            for (int ph = 0; ph < 6; ++ph) {                  // tau = 120 .. 125: the reference has run out
+                const int tau = 120 + ph;
+                const float x1 = xs[tau];
+                q[ph] = p2pack(0.0f, (ph == 0) ? xr[119] : 0.0f);
+                const p2 xx = p2pack(x1, x1);
+                a01 = p2add(a01, p2mul(xx, q[ph]));
+                a23 = p2add(a23, p2mul(xx, q[(ph + 4) % 6]));
+                a45 = p2add(a45, p2mul(xx, q[(ph + 2) % 6]));
+                a6 += x1 * p2hi(q[(ph + 1) % 6]);
+            }
+            dot[0] = p2lo(a01); dot[1] = p2hi(a01); dot[2] = p2lo(a23); dot[3] = p2hi(a23);
+            dot[4] = p2lo(a45); dot[5] = p2hi(a45); dot[6] = a6;
         }
         // reference energy of my frame: from the lane that holds its reference item
         const float engr = __shfl_sync(0xffffffffu, s2, base_f + st_n[my_f]);
