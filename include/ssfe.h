@@ -64,7 +64,8 @@ typedef struct {
     double  dither_scale;     /* 1e-06 (make_spect_f0.py:55)                                   */
     int32_t filtfilt_mode;    /* 0 = chunked parallel scan (default), 1 = one thread per
                                  utterance, sequential (validation aid; same arithmetic order
-                                 as scipy's C loop)                                            */
+                                 as scipy's C loop), 3 = the scan with its local passes walking
+                                 the recurrence instead of taking dot products (A/B aid)       */
     int32_t reserved;
 } ssfe_config;
 
@@ -133,6 +134,11 @@ int ssfe_mt_jump_taps(uint64_t unit_words, int level, int d, uint16_t *taps, int
  * Returns 0, or a negative code when (b6, a6) does not factor into stable real sections. */
 int ssfe_filt_cascade(const double *b6, const double *a6, const double *zi5, int chunk, double *sec, double *zic,
                       double *m);
+/* Taps of the scan's local passes: the final cascade state of a chunk entered with a ZERO state is
+ *   s[k] = sum_i g[k * chunk + i] * x[i],   g[k][i] = ((cascade state matrix)^(chunk-1-i) * input vector)[k],
+ * so the two local passes are five dot products per chunk instead of a walk of the recurrence.  sec15 = the
+ * sections ssfe_filt_cascade returned; g: [5][chunk].  Returns 0, or -1 for bad arguments. */
+int ssfe_filt_cascade_taps(const double *sec15, int chunk, double *g);
 
 /* (a3) utils.pySTFT(x) (utils.py:18-31) for 1-D inputs: reflect-pad 512, hop 256, periodic
  * Hann(1024), |rfft|.  wav_dev float32 concatenated, offsets host [n+1] (lengths as given, no

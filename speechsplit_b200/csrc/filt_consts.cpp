@@ -279,3 +279,41 @@ extern "C" int ssfe_filt_cascade(const double *b6, const double *a6, const doubl
     for (int i = 0; i < 25; ++i) m[i] = (double)P[i];
     return 0;
 }
+
+// Taps of the zero-state chunk finals.  A chunk's final cascade state from a ZERO entry state is linear in its
+// samples:  s = sum_i A_c^(chunk-1-i) B_c x[i].  The scan's local passes need nothing but s, so they evaluate these
+// five dot products (filt_dot_kernel) instead of walking the recurrence.
+//   sec15  the ROUNDED sections ssfe_filt_cascade returned (what Casc::step evaluates)
+//   g      [5][chunk]: g[k * chunk + i] = (A_c^(chunk-1-i) B_c)[k], rounded from 113 bits
+extern "C" int ssfe_filt_cascade_taps(const double *sec15, int chunk, double *g)
+{
+    if (!sec15 || !g || chunk < 1) return -1;
+    Sec s[3];
+    for (int k = 0; k < 3; ++k)
+        s[k] = {k == 0 ? 1 : 2, (q)sec15[k * 5 + 0], (q)sec15[k * 5 + 1], (q)sec15[k * 5 + 2], (q)sec15[k * 5 + 3],
+                (q)sec15[k * 5 + 4]};
+    q A0[4], B0[2], D0, A1[4], B1[2], D1, A2[4], B2[2], D2;
+    sec_ss(s[0], A0, B0, &D0);
+    sec_ss(s[1], A1, B1, &D1);
+    sec_ss(s[2], A2, B2, &D2);
+    q Ac[25];
+    for (int i = 0; i < 25; ++i) Ac[i] = 0;
+    Ac[0 * 5 + 0] = A0[0];
+    Ac[1 * 5 + 1] = A1[0]; Ac[1 * 5 + 2] = A1[1]; Ac[1 * 5 + 0] = B1[0];
+    Ac[2 * 5 + 1] = A1[2]; Ac[2 * 5 + 2] = A1[3]; Ac[2 * 5 + 0] = B1[1];
+    Ac[3 * 5 + 3] = A2[0]; Ac[3 * 5 + 4] = A2[1]; Ac[3 * 5 + 1] = B2[0]; Ac[3 * 5 + 0] = B2[0] * D1;
+    Ac[4 * 5 + 3] = A2[2]; Ac[4 * 5 + 4] = A2[3]; Ac[4 * 5 + 1] = B2[1]; Ac[4 * 5 + 0] = B2[1] * D1;
+    // input vector: x enters section 0 directly, section 1 through y0 = z0 + D0 x, section 2 through y1 = z1 + D1 y0
+    q v[5] = {B0[0], B1[0] * D0, B1[1] * D0, B2[0] * D1 * D0, B2[1] * D1 * D0};
+    for (int m = 0; m < chunk; ++m) {                 // v = A_c^m B_c belongs to sample chunk-1-m
+        for (int k = 0; k < 5; ++k) g[k * chunk + (chunk - 1 - m)] = (double)v[k];
+        q nx[5];
+        for (int i = 0; i < 5; ++i) {
+            q acc = 0;
+            for (int j = 0; j < 5; ++j) acc += Ac[i * 5 + j] * v[j];
+            nx[i] = acc;
+        }
+        for (int i = 0; i < 5; ++i) v[i] = nx[i];
+    }
+    return 0;
+}

@@ -27,12 +27,14 @@
 // ((z[i+1] + x*b) - y*a, no FMA contraction): bit-identical to scipy, a validation aid.
 #include "common.cuh"
 #include "mt_convert.cuh"
+#include "tma.cuh"
 #include <algorithm>
 
 namespace ssfe {
 
 extern "C" int ssfe_filt_cascade(const double *b6, const double *a6, const double *zi5, int chunk, double *sec,
                                  double *zic, double *m);     // filt_consts.cpp
+extern "C" int ssfe_filt_cascade_taps(const double *sec15, int chunk, double *g);
 
 constexpr int kChunk = 256;
 constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
@@ -445,6 +447,233 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
     }
 }
 
+// ---- local passes as dot products ----------------------------------------------------------------------
+// The local passes need only the FINAL state of every chunk entered with a zero state, and that is linear in the
+// chunk's samples:  s[k] = sum_i g[k][i] x[i]  with  g[k][i] = (A_c^(255-i) B_c)[k]  (filt_consts.cpp, 113-bit
+// algebra, |g| <= ~1).  So instead of walking the recurrence through a shared-memory transpose (13 dependent
+// fp64 operations per sample, the tile kernel above with FINAL = false: 3.3 + 2.3 ms on the full corpus) a warp
+// forms five dot products per chunk - lane l owns samples l + 32 q, its 40 taps stay in registers for the whole
+// kernel - 5 FMAs per sample, no dependent chain.  The partial sums of FOUR chunks (20 values per lane) are summed
+// over the lanes by two select-free halving steps and three butterflies (30 shuffle rounds instead of 100).  The
+// summation order is fixed by the lane layout alone, so a chunk's state does not depend on the batch it is in.
+// What is left is a streaming read, and the samples are staged by TMA: a group of four chunks is ONE contiguous run
+// (2 KB of PCM, 4 KB of y1), fetched by a single bulk copy from the 16-byte line its first sample lies in into one
+// of the warp's three stage buffers; every warp is its own producer (lane 0, two groups ahead, across tile and
+// utterance boundaries) and consumer, no block-level barrier.  (The first version took the samples with 32
+// plain loads per lane and group: 2 KB in flight per warp only between the reductions - 2.4 / 2.1 ms, 1.7 TB/s.)
+// Groups that touch the odd extension, the appended sample or the ragged end of an utterance (two of ~47 for a 3 s
+// utterance) take their samples element by element.
+__device__ double g_filt_taps[5 * kChunk];      // [k][i], see ssfe_filt_cascade_taps
+constexpr int kDotWarps = 4;
+constexpr int kDotGroup = 4;                    // chunks per group / reduction
+constexpr int kDotStages = 3;
+constexpr int kDotElems = kDotGroup * kChunk;   // samples per group
+
+template <typename RawT> constexpr int dot_stage_bytes() { return (kDotElems * static_cast<int>(sizeof(RawT)) + 16 + 127) / 128 * 128; }
+
+struct DotDesc {          // one per stage, written by the producer step, read by the consumer step of the same warp
+    long long state_idx;  // first of the group's 20 state values
+    int tile, r0, cnt, fast, off;
+    int pad;
+};
+
+struct DotTile {          // warp-uniform geometry of a tile (32 chunks of one utterance)
+    int u, sc, c_first, n_run, L, Lf, M;
+    long long xbase, ebase;
+    __device__ __forceinline__ void load(const FiltParams &p, const int *__restrict__ tile_off, const int *__restrict__ tile_map, int tile)
+    {
+        u = tile_map[tile];
+        sc = tile - tile_off[u];
+        c_first = p.chunk_off[u];
+        const int nch = p.chunk_off[u + 1] - c_first;
+        xbase = p.in_off[u];
+        const long long fbase = p.fix_off[u];
+        L = static_cast<int>(p.in_off[u + 1] - xbase);
+        Lf = static_cast<int>(p.fix_off[u + 1] - fbase);
+        M = Lf + 2 * kPadLen;
+        ebase = fbase + static_cast<long long>(u) * 2 * kPadLen;
+        n_run = min(32, nch - 1 - sc * 32);     // nobody consumes the carry out of the utterance's last chunk
+    }
+};
+
+template <int DTYPE, int PASS>
+__global__ void __launch_bounds__(kDotWarps * 32) filt_dot_kernel(const FiltParams p, const int *__restrict__ tile_off,
+                                                                  int n_tiles, const int *__restrict__ tile_map)
+{
+    using RawT = typename RawType<DTYPE, PASS>::T;
+    constexpr bool kTma = sizeof(RawT) <= 4;          // fp64 input (a validation dtype) is read element by element
+    constexpr int kStage = dot_stage_bytes<RawT>();
+    extern __shared__ __align__(128) unsigned char s_dot[];
+    __shared__ __align__(8) uint64_t s_bar[kDotWarps][kDotStages];
+    __shared__ DotDesc s_desc[kDotWarps][kDotStages];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_warps = gridDim.x * kDotWarps;
+    unsigned char *stage0 = s_dot + static_cast<size_t>(w) * kDotStages * kStage;
+    uint64_t *bar = s_bar[w];
+    DotDesc *desc = s_desc[w];
+    if (kTma && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kDotStages; ++i) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double gl[5][8];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gl[k][q] = g_filt_taps[k * kChunk + lane + 32 * q];
+    // Accumulator slot i of a lane belongs to chunk i ^ cx of the group, cx = lane bits 4:3.  With that, the first two
+    // reduction steps are halvings without a single select: a lane keeps slots 0-1 (then slot 0) and adds its partner's
+    // slots 2-3 (slot 1), which are the same chunks seen from the other side; the lanes with bits 4:3 = c end up with
+    // chunk c, five values summed over four lanes, and three butterfly steps over bits 2:0 finish them.
+    const int cx = (lane >> 3) & 3;
+    __syncwarp();
+
+    // ---- producer side: the warp's groups in order, (tile, r0) with tile = warp, warp + n_warps, ... ----------------
+    DotTile pt;
+    int p_tile = blockIdx.x * kDotWarps + w, p_r0 = 0;
+    auto settle = [&]() {                             // move to the next tile that has a group at p_r0
+        while (p_tile < n_tiles) {
+            pt.load(p, tile_off, tile_map, p_tile);
+            if (p_r0 < pt.n_run) break;
+            p_tile += n_warps;
+            p_r0 = 0;
+        }
+    };
+    settle();
+    auto produce = [&](int s) {
+        DotDesc d;
+        d.pad = 0;
+        if (p_tile >= n_tiles) {                      // the sentinel: no more groups
+            d.state_idx = 0; d.tile = -1; d.r0 = 0; d.cnt = 0; d.fast = 0; d.off = 0;
+        } else {
+            const int j0 = (pt.sc * 32 + p_r0) * kChunk;
+            d.tile = p_tile;
+            d.r0 = p_r0;
+            d.cnt = min(kDotGroup, pt.n_run - p_r0);
+            d.state_idx = (static_cast<long long>(pt.c_first) + pt.sc * 32 + p_r0) * 5;
+            d.fast = (d.cnt == kDotGroup) && (PASS == 1 || (j0 >= kPadLen && j0 + kDotElems <= kPadLen + pt.L));
+            d.off = 0;
+            if (kTma && d.fast) {
+                // lowest address of the group's run: forward x[xbase + j0 - 18 ...], backward y1[ebase + M - j0 - 1024 ...]
+                const RawT *src = (PASS == 0) ? static_cast<const RawT *>(p.x) + (pt.xbase + (j0 - kPadLen))
+                                              : reinterpret_cast<const RawT *>(p.y1f) + (pt.ebase + (pt.M - j0 - kDotElems));
+                const uintptr_t a = reinterpret_cast<uintptr_t>(src), a0 = a & ~static_cast<uintptr_t>(15);
+                const uint32_t bytes = static_cast<uint32_t>(((a + kDotElems * sizeof(RawT) + 15) & ~static_cast<uintptr_t>(15)) - a0);
+                d.off = static_cast<int>((a - a0) / sizeof(RawT));
+                if (lane == 0) {
+                    mbar_expect_tx(&bar[s], bytes);
+                    tma_load_1d(stage0 + s * kStage, reinterpret_cast<const void *>(a0), bytes, &bar[s]);
+                }
+            }
+            p_r0 += kDotGroup;
+            if (p_r0 >= pt.n_run) {
+                p_tile += n_warps;
+                p_r0 = 0;
+                settle();
+            }
+        }
+        if (lane == 0) desc[s] = d;
+    };
+#pragma unroll
+    for (int s = 0; s < kDotStages - 1; ++s) produce(s);
+    __syncwarp();
+
+    uint32_t parity = 0;                              // bit s: phase of stage s's barrier
+    for (int it = 0;; ++it) {
+        const int s = it % kDotStages;
+        produce((it + kDotStages - 1) % kDotStages);  // the stage the previous iteration released
+        __syncwarp();
+        const DotDesc d = desc[s];
+        if (d.tile < 0) break;
+        double val[kDotGroup * 5];
+#pragma unroll
+        for (int i = 0; i < kDotGroup * 5; ++i) val[i] = 0.0;
+        if (kTma && d.fast) {
+            mbar_wait(&bar[s], (parity >> s) & 1u);
+            parity ^= 1u << s;
+            const RawT *buf = reinterpret_cast<const RawT *>(stage0 + s * kStage) + d.off;
+#pragma unroll
+            for (int i = 0; i < kDotGroup; ++i) {
+                const int e0 = ((i ^ cx) << 8) + lane;              // kChunk == 256
+                const RawT *bi = buf + (PASS == 0 ? e0 : kDotElems - 1 - e0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double v = static_cast<double>(bi[PASS == 0 ? 32 * q : -32 * q]);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) val[i * 5 + k] = fma(gl[k][q], v, val[i * 5 + k]);
+                }
+            }
+        } else {
+            // element-wise groups: every position is mapped to a clamped source index, the 32 loads go out together, and
+            // extension, appended sample and validity are applied afterwards from the index arithmetic alone (as in the
+            // tile kernel) - taken one dependent load at a time, these two groups of an utterance cost a fifth of the kernel
+            DotTile ct;
+            ct.load(p, tile_off, tile_map, d.tile);
+            const int j0 = (ct.sc * 32 + d.r0) * kChunk;
+            const int L = ct.L, Lf = ct.Lf, M = ct.M;
+            auto src_index = [&](int j) -> int {             // position in the extended signal -> sample of x'
+                int nn = j - kPadLen;
+                if (j < kPadLen) nn = kPadLen - j;
+                else if (j >= kPadLen + Lf) nn = Lf - 2 - (j - kPadLen - Lf);
+                return nn;
+            };
+            double e0 = 0.0, e1 = 0.0;
+            if (PASS == 0) {
+                e0 = fixed_sample<DTYPE>(p.x, ct.xbase, L, 0);
+                e1 = fixed_sample<DTYPE>(p.x, ct.xbase, L, Lf - 1);
+            }
+            RawT raw[kDotGroup][8];
+#pragma unroll
+            for (int i = 0; i < kDotGroup; ++i)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = j0 + (i ^ cx) * kChunk + lane + 32 * q;
+                    if (PASS == 0) raw[i][q] = static_cast<const RawT *>(p.x)[ct.xbase + min(max(src_index(j), 0), L - 1)];
+                    else raw[i][q] = reinterpret_cast<const RawT *>(p.y1f)[ct.ebase + min(max(M - 1 - j, 0), M - 1)];
+                }
+#pragma unroll
+            for (int i = 0; i < kDotGroup; ++i)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = j0 + (i ^ cx) * kChunk + lane + 32 * q;
+                    double v = static_cast<double>(raw[i][q]);
+                    if (PASS == 0) {
+                        if (DTYPE == SSFE_I16) v *= (1.0 / 32768.0);
+                        if (src_index(j) >= L) v = 1e-06;                          // the appended sample
+                        if (j < kPadLen) v = __dsub_rn(2.0 * e0, v);
+                        else if (j >= kPadLen + Lf) v = __dsub_rn(2.0 * e1, v);
+                    }
+                    if ((i ^ cx) >= d.cnt || j >= M) v = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) val[i * 5 + k] = fma(gl[k][q], v, val[i * 5 + k]);
+                }
+        }
+        __syncwarp();                                 // every lane has read the stage: the next produce may refill it
+        static_assert(kDotGroup == 4 && kChunk == 256, "the reduction below is written for four chunks of 256");
+#pragma unroll
+        for (int i = 0; i < 10; ++i) val[i] += __shfl_xor_sync(0xffffffffu, val[i + 10], 16);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) val[i] += __shfl_xor_sync(0xffffffffu, val[i + 5], 8);
+#pragma unroll
+        for (int m = 4; m > 0; m >>= 1)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) val[i] += __shfl_xor_sync(0xffffffffu, val[i], m);
+        if ((lane & 7) == 0 && cx < d.cnt) {
+            // the PCM scale of the TMA path (raw int16 values), exact: a power of two; the element-wise path scales its samples
+            const double sc = (PASS == 0 && DTYPE == SSFE_I16 && d.fast) ? (1.0 / 32768.0) : 1.0;
+            double *dst = p.state + d.state_idx + cx * 5;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) dst[k] = val[k] * sc;
+        }
+    }
+}
+
+template <int DTYPE, int PASS> constexpr size_t dot_smem()
+{
+    using RawT = typename RawType<DTYPE, PASS>::T;
+    return sizeof(RawT) <= 4 ? static_cast<size_t>(kDotWarps) * kDotStages * dot_stage_bytes<RawT>() : 16;
+}
+
 // ---- carry ---------------------------------------------------------------------------------------------
 // Turn the zero-state finals into true chunk-entry states: z' = M z + s per chunk, M = A_c^256 of the cascade.
 // Its entries are O(10) and the recurrence is well conditioned, so this is plain fp64 (the DF2T realisation
@@ -574,14 +803,22 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
         if (dith_ready) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));
         return SSFE_OK;
     }
-    filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    // local passes: grid-stride over the tiles, a few tiles per warp so that the 40 tap loads amortise
+    const unsigned gd = static_cast<unsigned>(std::max(1, std::min((n_tiles + kDotWarps - 1) / kDotWarps, ctx->num_sms * 3)));
+    if (ctx->cfg.filtfilt_mode == 3)                                   // the recurrence-walking local pass (A/B, validation)
+        filt_tile_kernel<DTYPE, 0, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    else
+        filt_dot_kernel<DTYPE, 0><<<gd, kDotWarps * 32, dot_smem<DTYPE, 0>(), st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     filt_carry_kernel<DTYPE, 0><<<gu, kCarryWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     p.y1f = p.y1f_out;
-    filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    if (ctx->cfg.filtfilt_mode == 3)
+        filt_tile_kernel<DTYPE, 1, false><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    else
+        filt_dot_kernel<DTYPE, 1><<<gd, kDotWarps * 32, dot_smem<DTYPE, 1>(), st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     filt_carry_kernel<DTYPE, 1><<<gu, kCarryWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
@@ -684,6 +921,18 @@ int init_filtfilt(ssfe_ctx *ctx)
     c.wav_scale = ctx->cfg.wav_scale;
     c.dither_scale = ctx->cfg.dither_scale;
     SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_filt, &c, sizeof(c)));
+    {
+        std::vector<double> g(5 * kChunk);
+        if (ssfe_filt_cascade_taps(c.sec, kChunk, g.data()) != 0)
+            return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: taps of the local passes could not be formed");
+        SSFE_CUDA(ctx, cudaMemcpyToSymbol(g_filt_taps, g.data(), g.size() * sizeof(double)));
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(filt_dot_kernel<SSFE_F32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dot_smem<SSFE_F32, 0>())));
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(filt_dot_kernel<SSFE_F64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dot_smem<SSFE_F64, 0>())));
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(filt_dot_kernel<SSFE_I16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dot_smem<SSFE_I16, 0>())));
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(filt_dot_kernel<SSFE_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dot_smem<SSFE_F32, 1>())));
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(filt_dot_kernel<SSFE_F64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dot_smem<SSFE_F64, 1>())));
+        SSFE_CUDA(ctx, cudaFuncSetAttribute(filt_dot_kernel<SSFE_I16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dot_smem<SSFE_I16, 1>())));
+    }
     return SSFE_OK;
 }
 

@@ -105,3 +105,36 @@ def test_chunk_carry_is_plain_fp64():
         carried = m @ z + run(seg, np.zeros(5))          # what filt_carry_kernel computes
         assert np.abs(carried - true_next).max() <= 1e-12
         z = true_next
+
+
+def test_local_pass_taps_are_the_zero_state_finals():
+    """ssfe_filt_cascade_taps: the dot products filt_dot_kernel takes equal the recurrence walked from a zero state."""
+    b, a, zi, sec, zic, m = _cascade(256)
+    lib = _lib.load()
+    g = np.zeros((5, 256))
+    assert lib.ssfe_filt_cascade_taps(np.ascontiguousarray(sec).ctypes.data, 256, g.ctypes.data) == 0
+    assert lib.ssfe_filt_cascade_taps(None, 256, g.ctypes.data) == -1
+    assert np.abs(g).max() < 2.0 and np.abs(g[:, -1]).max() > 1e-3          # well scaled: a plain fp64 sum is enough
+
+    def run(xs):
+        z = np.zeros(5, np.longdouble)
+        s = sec.astype(np.longdouble)
+        for xn in xs.astype(np.longdouble):
+            y0 = s[0, 0] * xn + z[0]
+            z[0] = s[0, 1] * xn - s[0, 3] * y0
+            y1 = s[1, 0] * y0 + z[1]
+            z[1] = s[1, 1] * y0 - s[1, 3] * y1 + z[2]
+            z[2] = s[1, 2] * y0 - s[1, 4] * y1
+            y2 = s[2, 0] * y1 + z[3]
+            z[3] = s[2, 1] * y1 - s[2, 3] * y2 + z[4]
+            z[4] = s[2, 2] * y1 - s[2, 4] * y2
+        return np.asarray(z, np.float64)
+
+    rng = np.random.default_rng(5)
+    for x in (0.3 * rng.standard_normal(256) + 0.1, np.ones(256), np.eye(256)[0], np.eye(256)[255],
+              np.round(3000 * rng.standard_normal(256)) / 32768.0):
+        assert np.abs(g @ x - run(x)).max() <= 2e-13 * max(1.0, np.abs(x).max())
+    # one chunk further: M z + taps . x is the true next state (what carry + final pass rely on)
+    x = 0.2 * rng.standard_normal(512)
+    z1 = g @ x[:256]
+    assert np.abs(m @ z1 + g @ x[256:] - run(x)).max() <= 1e-12
