@@ -933,11 +933,10 @@ __device__ __forceinline__ float jump_cost(float ftemp, float ln2, float fdouble
     // double sum of the two floats (0.35 and a value below 8) is exact unless the smaller one is below 2^-29 of
     // the larger - where it cannot reach a rounding boundary of the float result either - so rounding it to float
     // is the correctly rounded float sum.  (Six fp64 conversions less on the Viterbi pass's critical path.)
+    // (the original's  if (ttemp > ft1) ttemp = ft1;  twice: a minimum of finite non-negative values, one FMNMX each)
     float ttemp = fabsf(ftemp);
-    float ft1 = fdouble + fabsf(ftemp + ln2);
-    if (ttemp > ft1) ttemp = ft1;
-    ft1 = fdouble + fabsf(ftemp - ln2);
-    if (ttemp > ft1) ttemp = ft1;
+    ttemp = fminf(ttemp, fdouble + fabsf(ftemp + ln2));
+    ttemp = fminf(ttemp, fdouble + fabsf(ftemp - ln2));
     return ttemp * freqwt;
 }
 
@@ -949,8 +948,13 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
     // records of 16 consecutive frames of each warp's utterance (see load_block below)
     __shared__ __align__(16) float s_bmp[kDpWarps][kDpBlk * kCMax];
     __shared__ __align__(16) int s_bloc[kDpWarps][kDpBlk * kCMax / 2];
-    __shared__ float s_bsr[kDpWarps][2 * kDpBlk];
+    __shared__ float s_bsr[kDpWarps][2 * kDpBlk];          // per frame of the block: voiced<-unvoiced, unvoiced<-voiced transition cost
     __shared__ unsigned char s_bnc[kDpWarps][kDpBlk];
+    // log(lag) of every candidate of the block's frames (0 for unvoiced / absent), row 0 = the last frame of the
+    // previous block: looked up once per block, sixteen frames side by side.  A frame takes its own row per lane and the
+    // previous frame's values as broadcast reads - neither depends on the Viterbi chain, only the accumulated costs
+    // (one shuffle per previous candidate) do.  (The first version shuffled lag, cost and the two halves of log(lag).)
+    __shared__ __align__(16) double s_blg[kDpWarps][(kDpBlk + 1) * kCMax];
     for (int i = threadIdx.x; i < kMaxLag; i += blockDim.x) s_log[i] = p.log_lag[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -967,7 +971,6 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
 
     float d_prev = 0.0f;
     int loc_prev = -1, ncandp = 0;
-    double lg_prev = 0.0;
     int head = -1, tail = 0, num_active = 0;
     int my_pre = 0;
     // Software pipeline in blocks of kDpBlk = 16 frames: while the frames of block b are processed out of shared
@@ -996,13 +999,32 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
         r_sr = (lane < kDpBlk) ? p.sta[gf0 + lane] : p.rr[gf0 + lane - kDpBlk];
         r_nc = (lane < kDpBlk) ? p.ncand[gf0 + lane] : 0;
     };
+    double *blg = s_blg[w];
     auto store_block = [&]() {                  // registers -> shared memory
+        if (lane < kCMax) blg[lane] = blg[kDpBlk * kCMax + lane];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kDpBlk * kCMax / 64; ++k) {
+            const int l0 = static_cast<short>(r_loc[k] & 0xffff), l1 = static_cast<short>(r_loc[k] >> 16);
+            double2 v;                          // (slack frames past the utterance hold arbitrary lags: range-checked)
+            v.x = (l0 > 0 && l0 < kMaxLag) ? s_log[l0] : 0.0;
+            v.y = (l1 > 0 && l1 < kMaxLag) ? s_log[l1] : 0.0;
+            *reinterpret_cast<double2 *>(blg + kCMax + 2 * (lane + 32 * k)) = v;
+        }
 #pragma unroll
         for (int k = 0; k < kDpBlk * kCMax / 32; ++k) bmp[lane + 32 * k] = r_mp[k];
 #pragma unroll
         for (int k = 0; k < kDpBlk * kCMax / 64; ++k) s_bloc[w][lane + 32 * k] = r_loc[k];
-        bsr[lane] = r_sr;
-        if (lane < kDpBlk) bnc[lane] = static_cast<unsigned char>(r_nc);
+        // the two voicing-transition costs of a frame depend on the frame alone: formed here for the block's 16
+        // frames side by side (lane = frame) instead of by every lane in every frame - a division and four more
+        // operations off the per-frame chain; same float expressions, same bits
+        const float rr_f = __shfl_down_sync(full_mask, r_sr, kDpBlk);
+        if (lane < kDpBlk) {
+            const float sta = r_sr;
+            bsr[lane] = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a / rr_f);            // voiced from unvoiced
+            bsr[kDpBlk + lane] = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr_f);   // unvoiced from voiced
+            bnc[lane] = static_cast<unsigned char>(r_nc);
+        }
         __syncwarp();
     };
     load_block(0);
@@ -1023,10 +1045,9 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
             const int ncand = bnc[fi];
             const int loc = (lane < ncand) ? bloc[fi * kCMax + lane] : -1;
             const float mp = (lane < ncand) ? bmp[fi * kCMax + lane] : 0.0f;
-            const float sta = bsr[fi], rr = bsr[kDpBlk + fi];
-            const double lg = (loc > 0) ? s_log[loc] : 0.0;
-            const float v_from_uv = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a / rr);
-            const float uv_from_v = c_rapt.tcost + (c_rapt.tfact_s * sta) + (c_rapt.tfact_a * rr);
+            const float v_from_uv = bsr[fi], uv_from_v = bsr[kDpBlk + fi];
+            const double lg = (lane < ncand) ? blg[(fi + 1) * kCMax + lane] : 0.0;
+            const double *lg_row = blg + fi * kCMax;             // the previous frame's
             float errmin = FLT_MAX;
             int minloc = 0;
             // Only the previous frame's live candidates are visited (typically 3-5 of the 20 slots; the count is
@@ -1040,11 +1061,10 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = j0 + jj;
-                        const int loc1 = __shfl_sync(full_mask, loc_prev, j);
+                        const double lg1 = lg_row[min(j, kCMax - 1)];             // same address in every lane
                         const float dp = __shfl_sync(full_mask, d_prev, j);
-                        const double lg1 = __shfl_sync(full_mask, lg_prev, j);
                         const float jc = jump_cost(static_cast<float>(lg - lg1), c_rapt.ln2, c_rapt.fdouble, c_rapt.freqwt);
-                        const bool v_prev = loc1 > 0;
+                        const bool v_prev = lg1 != 0.0;                            // lags are >= fs / 600 = 26: log(lag) > 0
                         const float ferr = v_cur ? (v_prev ? jc : v_from_uv) : (v_prev ? uv_from_v : 0.0f);
                         errs[jj] = (j < ncandp) ? ferr + dp : FLT_MAX;
                     }
@@ -1069,7 +1089,6 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
             if (lane < kCMax) ring[g & (kRing - 1)][lane] = static_cast<unsigned char>(my_pre);
             d_prev = dcur;
             loc_prev = loc;
-            lg_prev = lg;
             ncandp = ncand;
             head = g;
         }

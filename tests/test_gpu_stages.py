@@ -208,10 +208,11 @@ def test_fused_mel_frame_counts(fe):
 def _f0_cases():
     rng = np.random.default_rng(21)
     out = []
-    for T in (1, 7, 8, 9, 127, 128, 129, 188, 300, 1000, 3751):
+    for T in (1, 7, 8, 9, 10, 12, 127, 128, 129, 188, 300, 1000, 3751, 60000):   # 60000: past the warp kernel's planned tree
         f0 = rng.normal(5.0, 0.25, T).astype(np.float32)
         f0[rng.random(T) < 0.3] = np.float32(-1e10)
         out.append(f0)
+    out.append(rng.normal(5.0, 0.25, 2048).astype(np.float32))  # all voiced, a power of two
     out.append(np.full(50, -1e10, np.float32))                 # all unvoiced -> nan stats, output untouched
     one = np.full(20, -1e10, np.float32)
     one[3] = 5.0                                               # single voiced frame -> std 0 -> nan
