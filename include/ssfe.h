@@ -139,6 +139,9 @@ int ssfe_filt_cascade(const double *b6, const double *a6, const double *zi5, int
  * so the two local passes are five dot products per chunk instead of a walk of the recurrence.  sec15 = the
  * sections ssfe_filt_cascade returned; g: [5][chunk].  Returns 0, or -1 for bad arguments. */
 int ssfe_filt_cascade_taps(const double *sec15, int chunk, double *g);
+/* Powers of the chunk-to-chunk carry matrix, for the carry kernel's scan over runs of `run` chunks:
+ *   out[k][25] = (cascade state matrix)^(chunk * run * 2^k), k = 0 .. n_pow - 1, row-major.  Returns 0 or -1. */
+int ssfe_filt_cascade_powers(const double *sec15, int chunk, int run, int n_pow, double *out);
 
 /* (a3) utils.pySTFT(x) (utils.py:18-31) for 1-D inputs: reflect-pad 512, hop 256, periodic
  * Hann(1024), |rfft|.  wav_dev float32 concatenated, offsets host [n+1] (lengths as given, no

@@ -62,6 +62,7 @@ SIGNATURES = {
                                        ctypes.c_int, ctypes.c_int, vp]),
     "ssfe_filt_cascade": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
     "ssfe_filt_cascade_taps": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "ssfe_filt_cascade_powers": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "ssfe_mt_charpoly_terms": (ctypes.c_int, [vp, ctypes.c_int]),
     "ssfe_mt_jump_poly": (ctypes.c_int, [ctypes.c_uint64, vp]),
     "ssfe_mt_jump_taps": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int]),

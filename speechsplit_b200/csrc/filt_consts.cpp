@@ -285,6 +285,49 @@ extern "C" int ssfe_filt_cascade(const double *b6, const double *a6, const doubl
 // five dot products (filt_dot_kernel) instead of walking the recurrence.
 //   sec15  the ROUNDED sections ssfe_filt_cascade returned (what Casc::step evaluates)
 //   g      [5][chunk]: g[k * chunk + i] = (A_c^(chunk-1-i) B_c)[k], rounded from 113 bits
+namespace {
+// cascade state matrix A_c and input vector B_c of the rounded sections (what Casc::step evaluates)
+void cascade_ab(const double *sec15, q *Ac, q *Bc)
+{
+    Sec s[3];
+    for (int k = 0; k < 3; ++k)
+        s[k] = {k == 0 ? 1 : 2, (q)sec15[k * 5 + 0], (q)sec15[k * 5 + 1], (q)sec15[k * 5 + 2], (q)sec15[k * 5 + 3],
+                (q)sec15[k * 5 + 4]};
+    q A0[4], B0[2], D0, A1[4], B1[2], D1, A2[4], B2[2], D2;
+    sec_ss(s[0], A0, B0, &D0);
+    sec_ss(s[1], A1, B1, &D1);
+    sec_ss(s[2], A2, B2, &D2);
+    for (int i = 0; i < 25; ++i) Ac[i] = 0;
+    Ac[0 * 5 + 0] = A0[0];
+    Ac[1 * 5 + 1] = A1[0]; Ac[1 * 5 + 2] = A1[1]; Ac[1 * 5 + 0] = B1[0];
+    Ac[2 * 5 + 1] = A1[2]; Ac[2 * 5 + 2] = A1[3]; Ac[2 * 5 + 0] = B1[1];
+    Ac[3 * 5 + 3] = A2[0]; Ac[3 * 5 + 4] = A2[1]; Ac[3 * 5 + 1] = B2[0]; Ac[3 * 5 + 0] = B2[0] * D1;
+    Ac[4 * 5 + 3] = A2[2]; Ac[4 * 5 + 4] = A2[3]; Ac[4 * 5 + 1] = B2[1]; Ac[4 * 5 + 0] = B2[1] * D1;
+    // x enters section 0 directly, section 1 through y0 = z0 + D0 x, section 2 through y1 = z1 + D1 y0
+    Bc[0] = B0[0]; Bc[1] = B1[0] * D0; Bc[2] = B1[1] * D0; Bc[3] = B2[0] * D1 * D0; Bc[4] = B2[1] * D1 * D0;
+}
+}  // namespace
+
+// Powers of the chunk-to-chunk carry matrix for the carry kernel's scan over runs of chunks:
+//   out[k][25] = A_c^(chunk * run * 2^k),  k = 0 .. n_pow - 1   (row-major, rounded from 113 bits)
+extern "C" int ssfe_filt_cascade_powers(const double *sec15, int chunk, int run, int n_pow, double *out)
+{
+    if (!sec15 || !out || chunk < 1 || run < 1 || n_pow < 1 || n_pow > 16) return -1;
+    q Ac[25], Bc[5], P[25], T[25];
+    cascade_ab(sec15, Ac, Bc);
+    for (int i = 0; i < 25; ++i) P[i] = (i % 6 == 0) ? 1 : 0;
+    for (long long k = 0; k < (long long)chunk * run; ++k) {
+        mat5_mul(Ac, P, T);
+        std::memcpy(P, T, sizeof(P));
+    }
+    for (int k = 0; k < n_pow; ++k) {
+        for (int i = 0; i < 25; ++i) out[k * 25 + i] = (double)P[i];
+        mat5_mul(P, P, T);
+        std::memcpy(P, T, sizeof(P));
+    }
+    return 0;
+}
+
 extern "C" int ssfe_filt_cascade_taps(const double *sec15, int chunk, double *g)
 {
     if (!sec15 || !g || chunk < 1) return -1;

@@ -35,6 +35,7 @@ namespace ssfe {
 extern "C" int ssfe_filt_cascade(const double *b6, const double *a6, const double *zi5, int chunk, double *sec,
                                  double *zic, double *m);     // filt_consts.cpp
 extern "C" int ssfe_filt_cascade_taps(const double *sec15, int chunk, double *g);
+extern "C" int ssfe_filt_cascade_powers(const double *sec15, int chunk, int run, int n_pow, double *out);
 
 constexpr int kChunk = 256;
 constexpr int kPadLen = 18;       // 3 * max(len(a), len(b))
@@ -45,6 +46,7 @@ struct FiltConsts {
     double sec[15];               // cascade sections [3][b0, b1, b2, a1, a2] (section 0 is first order)
     double zic[5];                // cascade state equivalent to zi
     double mc[25];                // A_c^kChunk, row-major
+    double mp[5][25];             // A_c^(kChunk * 8 * 2^k): the carry kernel's scan over runs of eight chunks
     double wav_scale, dither_scale;
 };
 
@@ -696,28 +698,40 @@ template <int DTYPE, int PASS> constexpr size_t dot_smem()
 // Turn the zero-state finals into true chunk-entry states: z' = M z + s per chunk, M = A_c^256 of the cascade.
 // Its entries are O(10) and the recurrence is well conditioned, so this is plain fp64 (the DF2T realisation
 // needed double-double here, five lanes per utterance and a warp-wide scan for long utterances).
-// A QUARTER-WARP per utterance: the zero-state finals of 8 chunks are fetched by its 8 lanes at once (and the next
-// 8 while these are consumed), staged in shared memory, and every lane walks the 8 dependent steps redundantly - a
-// five-deep FMA chain each, no shuffles; lane i keeps the state it sees at step i, so the entry states leave with
-// one store round per tile.  (One thread per utterance with a one-step prefetch paid a trip to L2 per chunk: 65 us
-// per pass for a single 3 s utterance and 1.3 ms for a batch of 60 s ones; a whole warp per utterance did the work
-// 32 times over and cost the full corpus 0.3 ms per pass.  This takes ~7 us for one utterance, 0.1 ms for 3 751
-// chunks, and the full corpus as long as the one-thread version.)  Control flow is uniform across the warp's four
-// utterances: the tile loop runs to the longest of them, everything else is predicated.
-constexpr int kCarryWarps = 4, kCarrySub = 4, kCarryTile = 8;
+// A WARP per utterance, 256 chunks per round, as a three-phase scan of its own: lane l owns the run of chunks
+// 8 l .. 8 l + 7; (1) it walks its run from a zero state (8 dependent mat-vecs); (2) the 32 run totals are combined
+// by a Kogge-Stone scan with the precomputed powers M^8, M^16, ... M^128 (five steps of five shuffled doubles and a
+// mat-vec; the round's entry state rides in lane 0's total); (3) it walks its run again from the true entry state
+// and keeps the state before every chunk.  21 dependent mat-vecs per 256 chunks instead of 256: a 3 s utterance's
+// 188 chunks take ~3 us instead of 20 (a quarter-warp per utterance walking the chunks eight at a time was the
+// previous version: 7 us warm, 20 us in the ncu launch list, 0.22 ms per pass on the full corpus).  Finals and entry
+// states cross shared memory so that global traffic is coalesced (a lane's run is 320 contiguous bytes).
+constexpr int kCarryWarps = 4, kCarryRun = 8, kCarryPow = 5;
+constexpr int kCarryStride = kCarryRun * 5 + 1;       // doubles per lane row in shared memory (odd: conflict-free)
+
+__device__ __forceinline__ void carry_matvec(const double *__restrict__ m, const double (&z)[5], const double (&add)[5], double (&out)[5])
+{
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        double acc = add[r];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc = fma(m[r * 5 + k], z[k], acc);
+        out[r] = acc;
+    }
+}
 
 template <int DTYPE, int PASS>
 __global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_kernel(const FiltParams p)
 {
-    __shared__ double s_fin[kCarryWarps][kCarrySub * kCarryTile * 5];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane >> 3, l8 = lane & 7;
-    const int u = (blockIdx.x * kCarryWarps + w) * kCarrySub + sub;
-    const bool live = u < p.n;
-    int c0 = 0, nc = 0;
-    double x0 = 0.0;
-    if (live) {
-        c0 = p.chunk_off[u];
-        nc = p.chunk_off[u + 1] - c0;
+    __shared__ double s_st[kCarryWarps][32 * kCarryStride];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int u = blockIdx.x * kCarryWarps + w;
+    if (u >= p.n) return;
+    double *st = s_st[w];
+    const int c0 = p.chunk_off[u];
+    const int nc = p.chunk_off[u + 1] - c0;
+    double x0;
+    {
         const int64_t L = p.in_off[u + 1] - p.in_off[u];
         const int64_t fbase = p.fix_off[u];
         const int64_t Lf = p.fix_off[u + 1] - fbase;
@@ -726,53 +740,86 @@ __global__ void __launch_bounds__(kCarryWarps * 32) filt_carry_kernel(const Filt
         if (PASS == 0) x0 = ext_sample<DTYPE>(p.x, p.in_off[u], L, Lf, 0);
         else x0 = static_cast<double>(p.y1f[ebase + M - 1]);
     }
-    const int nmax = __reduce_max_sync(0xffffffffu, nc);
-    double z[5];
+    double ze[5];                                                 // entry state of the round's first chunk
 #pragma unroll
-    for (int i = 0; i < 5; ++i) z[i] = c_filt.zic[i] * x0;       // scipy's zi * x[0], in cascade coordinates
+    for (int i = 0; i < 5; ++i) ze[i] = c_filt.zic[i] * x0;       // scipy's zi * x[0], in cascade coordinates
     const double *__restrict__ s_in = p.state + static_cast<int64_t>(c0) * 5;
     double *__restrict__ zout = p.zin + static_cast<int64_t>(c0) * 5;
-    double *fin = s_fin[w] + sub * (kCarryTile * 5);
-    double pre[5];
-    auto load_tile = [&](int t0) {                                // finals of chunks t0 .. t0 + 7 (the last chunk has none)
+    constexpr int kRound = 32 * kCarryRun, kVals = kCarryRun * 5;
+    for (int base = 0; base < nc; base += kRound) {
+        // finals of the round's chunks (the utterance's last chunk has none), coalesced -> one row per lane
+#pragma unroll 8
+        for (int j = 0; j < kVals; ++j) {
+            const int e = lane + 32 * j, ch = base + e / 5;
+            const double v = (ch + 1 < nc) ? s_in[static_cast<int64_t>(base) * 5 + e] : 0.0;
+            st[(e / kVals) * kCarryStride + (e % kVals)] = v;
+        }
+        __syncwarp();
+        double sv[kCarryRun][5];
+        const double *row = st + lane * kCarryStride;
+#pragma unroll
+        for (int i = 0; i < kCarryRun; ++i)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sv[i][k] = row[i * 5 + k];
+        // (1) my run from a zero state
+        double t[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) t[k] = sv[0][k];
+#pragma unroll
+        for (int i = 1; i < kCarryRun; ++i) {
+            double o[5];
+            carry_matvec(c_filt.mc, t, sv[i], o);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) t[k] = o[k];
+        }
+        if (lane == 0) {                                          // the round's entry state enters through lane 0
+            double o[5];
+            carry_matvec(c_filt.mp[0], ze, t, o);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) t[k] = o[k];
+        }
+        // (2) inclusive scan of the run totals: t_l <- M^(8 d) t_(l-d) + t_l for d = 1, 2, 4, 8, 16
+#pragma unroll
+        for (int lv = 0; lv < kCarryPow; ++lv) {
+            const int d = 1 << lv;
+            double up[5], o[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) up[k] = __shfl_up_sync(0xffffffffu, t[k], d);
+            carry_matvec(c_filt.mp[lv], up, t, o);
+            if (lane >= d) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) t[k] = o[k];
+            }
+        }
+        // t of lane l is now the entry state of run l + 1
+        double z[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const int idx = l8 + kCarryTile * k, ch = t0 + idx / 5;
-            pre[k] = (ch + 1 < nc) ? s_in[static_cast<int64_t>(t0) * 5 + idx] : 0.0;
+            const double prev = __shfl_up_sync(0xffffffffu, t[k], 1);
+            z[k] = (lane == 0) ? ze[k] : prev;
+            ze[k] = __shfl_sync(0xffffffffu, t[k], 31);           // entry state of the next round
         }
-    };
-    load_tile(0);
-    for (int t0 = 0; t0 < nmax; t0 += kCarryTile) {
+        __syncwarp();                                             // every lane has taken its finals out of its row
+        // (3) my run from its true entry state; the row now collects the entry states
+        double *orow = st + lane * kCarryStride;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) fin[l8 + kCarryTile * k] = pre[k];
+        for (int i = 0; i < kCarryRun; ++i) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) orow[i * 5 + k] = z[k];
+            if (i + 1 < kCarryRun) {
+                double o[5];
+                carry_matvec(c_filt.mc, z, sv[i], o);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) z[k] = o[k];
+            }
+        }
         __syncwarp();
-        load_tile(t0 + kCarryTile);                               // in flight during the steps below (predicated by nc)
-        const int cnt = nc - t0;                                  // chunks of this utterance in the tile (may be <= 0)
-        double keep[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int i = 0; i < kCarryTile; ++i) {
-            if (l8 == i) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) keep[k] = z[k];       // z_in of chunk t0 + i
-            }
-            if (i + 1 < cnt) {
-                double t[5];
-#pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    double acc = fin[i * 5 + r];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) acc = fma(c_filt.mc[r * 5 + k], z[k], acc);
-                    t[r] = acc;
-                }
-#pragma unroll
-                for (int r = 0; r < 5; ++r) z[r] = t[r];
-            }
+#pragma unroll 8
+        for (int j = 0; j < kVals; ++j) {
+            const int e = lane + 32 * j, ch = base + e / 5;
+            if (ch < nc) zout[static_cast<int64_t>(base) * 5 + e] = st[(e / kVals) * kCarryStride + (e % kVals)];
         }
-        if (l8 < cnt) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) zout[static_cast<int64_t>(t0 + l8) * 5 + k] = keep[k];
-        }
-        __syncwarp();                                             // fin is rewritten by the next tile
+        __syncwarp();                                             // the rows are refilled by the next round
     }
 }
 
@@ -809,7 +856,7 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
 {
     const unsigned gc = (p.n_chunks + kFiltThreads - 1) / kFiltThreads;
     const unsigned gt = (n_tiles + kFiltWarps - 1) / kFiltWarps;
-    const unsigned gu = (p.n + kCarryWarps * kCarrySub - 1) / (kCarryWarps * kCarrySub);
+    const unsigned gu = (p.n + kCarryWarps - 1) / kCarryWarps;
     cudaStream_t st = ctx->stream;
     if (sequential) {
         filt_chunk_kernel<DTYPE, 0, true><<<gc, kFiltThreads, 0, st>>>(p);
@@ -939,6 +986,9 @@ int init_filtfilt(ssfe_ctx *ctx)
     }
     c.wav_scale = ctx->cfg.wav_scale;
     c.dither_scale = ctx->cfg.dither_scale;
+    static_assert(kCarryPow == 5 && kCarryRun == 8, "FiltConsts::mp holds five powers of the eight-chunk carry");
+    if (ssfe_filt_cascade_powers(c.sec, kChunk, kCarryRun, kCarryPow, &c.mp[0][0]) != 0)
+        return set_error(ctx, SSFE_ERR_INVALID, "filtfilt: powers of the carry matrix could not be formed");
     SSFE_CUDA(ctx, cudaMemcpyToSymbol(c_filt, &c, sizeof(c)));
     {
         std::vector<double> g(5 * kChunk);

@@ -138,3 +138,28 @@ def test_local_pass_taps_are_the_zero_state_finals():
     x = 0.2 * rng.standard_normal(512)
     z1 = g @ x[:256]
     assert np.abs(m @ z1 + g @ x[256:] - run(x)).max() <= 1e-12
+
+
+def test_carry_powers_for_the_scan_over_runs():
+    """ssfe_filt_cascade_powers: M^8, M^16, ... for the carry kernel's Kogge-Stone scan over runs of eight chunks."""
+    b, a, zi, sec, zic, m = _cascade(256)
+    lib = _lib.load()
+    pw = np.zeros((5, 5, 5))
+    assert lib.ssfe_filt_cascade_powers(np.ascontiguousarray(sec).ctypes.data, 256, 8, 5, pw.ctypes.data) == 0
+    assert lib.ssfe_filt_cascade_powers(np.ascontiguousarray(sec).ctypes.data, 256, 8, 0, pw.ctypes.data) == -1
+    ref = np.linalg.matrix_power(m.astype(np.longdouble), 8)
+    for k in range(5):
+        # (ref comes from the ROUNDED m: its 1e-16 rounding grows with the power)
+        assert np.abs(pw[k] - np.asarray(ref, np.float64)).max() <= 1e-11 * max(1.0, np.abs(pw[k]).max())
+        ref = ref @ ref
+    # the scan's algebra: entry state of run l+1 = M^8 (entry of run l) + (run l walked from zero)
+    rng = np.random.default_rng(9)
+    s = rng.standard_normal((16, 5))
+    z = rng.standard_normal(5)
+    seq = [z]
+    for c in range(16):
+        seq.append(m @ seq[-1] + s[c])
+    t0 = np.zeros(5)
+    for c in range(8):
+        t0 = m @ t0 + s[c]
+    assert np.abs(pw[0] @ z + t0 - seq[8]).max() <= 1e-11 * max(1.0, np.abs(seq[8]).max())
