@@ -72,6 +72,7 @@ struct FiltParams {
     int dith_raw;                 // dith holds raw MT19937 word pairs
     int dith_f32;                 // dith holds ONE raw MT19937 word per sample (mt_convert.cuh: mt_a_to_dither_f32)
     int dith_pf;                  // prefetch of the dither words: 0 none, 1 into L2, 2 into L1
+    int rows;                     // chunks per tile (= per warp): 32, or 8 for a batch too small to fill the GPU
 };
 
 __constant__ FiltConsts c_filt;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(kFiltThreads) filt_chunk_kernel(const FiltPara
 constexpr int kTileW = 32;                   // samples per row and sub-step
 constexpr int kTileStride = kTileW + 1;      // doubles per tile row (column reads are conflict-free)
 constexpr int kFiltWarps = 4;
+constexpr int kSmallRows = 8;                // chunks per tile for small batches (see filtfilt_run)
 #ifndef SSFE_FILT_BWD_CTAS
 #define SSFE_FILT_BWD_CTAS 4      // CTAs per SM the backward final pass is compiled for (5 spills 120 bytes; A/B in profiles/)
 #endif
@@ -220,19 +222,19 @@ template <int DTYPE, int PASS> struct RawType { using T = float; };      // pass
 template <> struct RawType<SSFE_I16, 0> { using T = short; };
 template <> struct RawType<SSFE_F64, 0> { using T = double; };
 
-template <int DTYPE, int PASS, bool FINAL>
+template <int DTYPE, int PASS, bool FINAL, int ROWS = 32>
 __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : SSFE_FILT_BWD_CTAS)) filt_tile_kernel(const FiltParams p, const int *__restrict__ tile_off,
                                                                      int n_tiles, const int *__restrict__ tile_map)
 {
-    __shared__ double s_tile[kFiltWarps][kTileW * kTileStride];
+    __shared__ double s_tile[kFiltWarps][ROWS * kTileStride];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tile = blockIdx.x * kFiltWarps + w;
     if (tile >= n_tiles) return;
     double *tl = s_tile[w];
     const int u = tile_map[tile];
-    const int sc = tile - tile_off[u];                         // super-chunk (32 chunks) inside the utterance
+    const int sc = tile - tile_off[u];                         // super-chunk (ROWS chunks) inside the utterance
     const int nch = p.chunk_off[u + 1] - p.chunk_off[u];
-    const int c = sc * 32 + lane;                              // this lane's chunk
+    const int c = sc * ROWS + lane;                            // this lane's chunk
     const int64_t xbase = p.in_off[u];
     const int64_t fbase = p.fix_off[u];
     // positions inside one utterance fit 32 bits (checked on the host); 64-bit only for the bases
@@ -240,9 +242,9 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
     const int Lf = static_cast<int>(p.fix_off[u + 1] - fbase);
     const int M = Lf + 2 * kPadLen;
     const int64_t ebase = fbase + static_cast<int64_t>(u) * 2 * kPadLen;
-    const int jt = sc * 32 * kChunk;                           // first sample of the super-chunk
-    const int rows = min(32, nch - sc * 32);                   // chunks present in this tile
-    const bool have = c < nch;
+    const int jt = sc * ROWS * kChunk;                         // first sample of the super-chunk
+    const int rows = min(ROWS, nch - sc * ROWS);               // chunks present in this tile
+    const bool have = lane < ROWS && c < nch;
     const int j0 = c * kChunk;
     const bool last_chunk = have && (j0 + kChunk >= M);
     const bool run = have && (FINAL || !last_chunk);           // nobody consumes the carry of the last chunk
@@ -276,12 +278,12 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
     // in-order warp wait for every load in turn.  (2) The fetch for sub-tile s+1 is issued BEFORE the
     // recurrence of sub-tile s runs, so the ~1-2 us of DRAM latency hide behind ~2000 cycles of fp64.
     using RawT = typename RawType<DTYPE, PASS>::T;
-    RawT raw[32];
+    RawT raw[ROWS];
     auto is_fast = [&](int sub) -> bool {
         const int js = jt + sub * kTileW;
-        if (rows != 32) return false;
-        if (PASS == 0) return (js >= kPadLen) && (js + 31 * kChunk + kTileW <= kPadLen + L);
-        return js + 31 * kChunk + kTileW <= M;
+        if (rows != ROWS) return false;
+        if (PASS == 0) return (js >= kPadLen) && (js + (ROWS - 1) * kChunk + kTileW <= kPadLen + L);
+        return js + (ROWS - 1) * kChunk + kTileW <= M;
     };
     // Edge tiles (the first tile of an utterance touches the 18 reflected samples, the last one is
     // ragged) are a third of all tiles for 3 s utterances, so they get the same treatment: every
@@ -299,20 +301,20 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
             if (fast_path) {
                 const RawT *xs = static_cast<const RawT *>(p.x) + (xbase + (js - kPadLen) + lane);
 #pragma unroll
-                for (int r = 0; r < 32; ++r) raw[r] = xs[r * kChunk];
+                for (int r = 0; r < ROWS; ++r) raw[r] = xs[r * kChunk];
             } else {
                 const RawT *xs = static_cast<const RawT *>(p.x) + xbase;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) raw[r] = xs[min(max(src_index(js + r * kChunk + lane), 0), L - 1)];
+                for (int r = 0; r < ROWS; ++r) raw[r] = xs[min(max(src_index(js + r * kChunk + lane), 0), L - 1)];
             }
         } else {
             if (fast_path) {
                 const float *ys = y1 + (M - 1 - js - lane);          // reversed: row r is kChunk samples earlier
 #pragma unroll
-                for (int r = 0; r < 32; ++r) raw[r] = ys[-r * kChunk];
+                for (int r = 0; r < ROWS; ++r) raw[r] = ys[-r * kChunk];
             } else {
 #pragma unroll
-                for (int r = 0; r < 32; ++r)
+                for (int r = 0; r < ROWS; ++r)
                     raw[r] = y1[min(max(M - 1 - (js + r * kChunk + lane), 0), M - 1)];
             }
         }
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
     // are used, they were the backward final pass's largest stall (70 % of its stall samples: the words come straight
     // from HBM, mt_walk_kernel wrote them a pass ago); a prefetch per lane sends them on their way one recurrence earlier.
     auto prefetch_dither = [&](int js) {
-        if (!(FINAL && PASS == 1) || !dith || !p.dith_pf) return;
+        if (!(FINAL && PASS == 1) || !dith || !p.dith_pf || lane >= ROWS) return;
         const int nb = M - 1 - kPadLen - js - lane * kChunk;
         if (nb - 31 < 0 || nb >= Lf) return;
         if (p.dith_pf == 1) {
@@ -345,14 +347,14 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
         const bool fast = is_fast(sub);
         if (fast) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
                 double v = static_cast<double>(raw[r]);
                 if (PASS == 0 && DTYPE == SSFE_I16) v *= (1.0 / 32768.0);
                 tl[r * kTileStride + lane] = v;
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
                 const int j = jsub + r * kChunk + lane;
                 double v = static_cast<double>(raw[r]);
                 if (PASS == 0) {
@@ -387,12 +389,12 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
             bool fast_out = fast;
             if (PASS == 1) {
                 // all 32 row segments map to output samples (none in the 18-sample pads)
-                const int n_hi = M - 1 - kPadLen - jsub, n_lo = n_hi - 31 * kChunk - (kTileW - 1);
+                const int n_hi = M - 1 - kPadLen - jsub, n_lo = n_hi - (ROWS - 1) * kChunk - (kTileW - 1);
                 fast_out = fast && n_lo >= 0 && n_hi < Lf && dith && wavp && !p.y && !p.wav && !p.wav64;
             }
             if (fast_out && PASS == 0) {
 #pragma unroll
-                for (int r = 0; r < 32; ++r) y1o[jsub + r * kChunk + lane] = static_cast<float>(tl[r * kTileStride + lane]);
+                for (int r = 0; r < ROWS; ++r) y1o[jsub + r * kChunk + lane] = static_cast<float>(tl[r * kTileStride + lane]);
             } else if (fast_out) {
                 // production path of the backward pass: wav = y * 0.96 + (U - 0.5) * 1e-06 -> f32 segment; the
                 // dither arrives as one raw generator word per sample (mt_walk_kernel<true>), tempering and the
@@ -402,25 +404,25 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
                 // then: 3 CTAs per SM instead of 4, and the pass got 4.5 ms SLOWER on the full corpus.
                 const int n0 = M - 1 - kPadLen - jsub - lane;
                 const uint32_t *dr = dith + n0;
-                uint32_t dv[32];
+                uint32_t dv[ROWS];
 #pragma unroll
-                for (int r = 0; r < 32; ++r) dv[r] = dr[-r * kChunk];
+                for (int r = 0; r < ROWS; ++r) dv[r] = dr[-r * kChunk];
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
+                for (int r = 0; r < ROWS; ++r) {
                     const double y = tl[r * kTileStride + lane];
                     wavp[n0 - r * kChunk] = static_cast<float>(
                         __dadd_rn(__dmul_rn(y, c_filt.wav_scale), static_cast<double>(mt_a_to_dither_f32(dv[r], dscale))));
                 }
             } else if (PASS == 1 && dith && wavp && !p.y && !p.wav && !p.wav64) {
                 // edge tile of the production path: same combine, dither words fetched together
-                uint32_t dv[32];
+                uint32_t dv[ROWS];
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
+                for (int r = 0; r < ROWS; ++r) {
                     const int nidx = M - 1 - kPadLen - (jsub + r * kChunk + lane);
                     dv[r] = dith[min(max(nidx, 0), Lf - 1)];
                 }
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
+                for (int r = 0; r < ROWS; ++r) {
                     const int j = jsub + r * kChunk + lane;
                     const int nidx = M - 1 - kPadLen - j;
                     if (r < rows && j < M && nidx >= 0 && nidx < Lf) {
@@ -512,7 +514,7 @@ struct DotTile {          // warp-uniform geometry of a tile (32 chunks of one u
         Lf = static_cast<int>(p.fix_off[u + 1] - fbase);
         M = Lf + 2 * kPadLen;
         ebase = fbase + static_cast<long long>(u) * 2 * kPadLen;
-        n_run = min(32, nch - 1 - sc * 32);     // nobody consumes the carry out of the utterance's last chunk
+        n_run = min(p.rows, nch - 1 - sc * p.rows);   // nobody consumes the carry out of the utterance's last chunk
     }
 };
 
@@ -566,11 +568,11 @@ __global__ void __launch_bounds__(kDotWarps * 32) filt_dot_kernel(const FiltPara
         if (p_tile >= n_tiles) {                      // the sentinel: no more groups
             d.state_idx = 0; d.tile = -1; d.r0 = 0; d.cnt = 0; d.fast = 0; d.off = 0;
         } else {
-            const int j0 = (pt.sc * 32 + p_r0) * kChunk;
+            const int j0 = (pt.sc * p.rows + p_r0) * kChunk;
             d.tile = p_tile;
             d.r0 = p_r0;
             d.cnt = min(kDotGroup, pt.n_run - p_r0);
-            d.state_idx = (static_cast<long long>(pt.c_first) + pt.sc * 32 + p_r0) * 5;
+            d.state_idx = (static_cast<long long>(pt.c_first) + pt.sc * p.rows + p_r0) * 5;
             d.fast = (d.cnt == kDotGroup) && (PASS == 1 || (j0 >= kPadLen && j0 + kDotElems <= kPadLen + pt.L));
             d.off = 0;
             if (kTma && d.fast) {
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(kDotWarps * 32) filt_dot_kernel(const FiltPara
             // tile kernel) - taken one dependent load at a time, these two groups of an utterance cost a fifth of the kernel
             DotTile ct;
             ct.load(p, tile_off, tile_map, d.tile);
-            const int j0 = (ct.sc * 32 + d.r0) * kChunk;
+            const int j0 = (ct.sc * p.rows + d.r0) * kChunk;
             const int L = ct.L, Lf = ct.Lf, M = ct.M;
             auto src_index = [&](int j) -> int {             // position in the extended signal -> sample of x'
                 int nn = j - kPadLen;
@@ -877,7 +879,10 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     SSFE_LAUNCHED(ctx);
     filt_carry_kernel<DTYPE, 0><<<gu, kCarryWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
-    filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    if (p.rows == kSmallRows)
+        filt_tile_kernel<DTYPE, 0, true, kSmallRows><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    else
+        filt_tile_kernel<DTYPE, 0, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     p.y1f = p.y1f_out;
     if (ctx->cfg.filtfilt_mode == 3)
@@ -888,7 +893,10 @@ static int filtfilt_typed(ssfe_ctx *ctx, FiltParams p, bool sequential, cudaEven
     filt_carry_kernel<DTYPE, 1><<<gu, kCarryWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     if (dith_ready) SSFE_CUDA(ctx, cudaStreamWaitEvent(st, dith_ready, 0));   // join the dither stream
-    filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    if (p.rows == kSmallRows)
+        filt_tile_kernel<DTYPE, 1, true, kSmallRows><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
+    else
+        filt_tile_kernel<DTYPE, 1, true><<<gt, kFiltWarps * 32, 0, st>>>(p, tile_off, n_tiles, tile_map);
     SSFE_LAUNCHED(ctx);
     if (dith_ready) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_dith_free, st));   // the dither buffer may be refilled
     return SSFE_OK;
@@ -900,6 +908,14 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     if (n == 0) return SSFE_OK;
     const bool sequential = ctx->cfg.filtfilt_mode == 1;
     std::vector<int> chunk_off(n + 1), tile_off(n + 1);
+    // Chunks per tile.  A warp walks its tile's chunks side by side, one lane each, and a chunk is 8 sub-tiles of
+    // load / recurrence / store in a row whatever the tile holds - for a batch that cannot fill the GPU (one 3 s
+    // utterance is 6 tiles of 32) tiles of 8 chunks spread the rows over four times the warps: the load and store
+    // phases shrink fourfold, the recurrence phase is a latency chain either way.
+    int64_t est_tiles = 0;
+    for (int i = 0; i < n && !sequential; ++i)
+        est_tiles += ((fix_off_host[i + 1] - fix_off_host[i] + 2 * kPadLen + kChunk - 1) / kChunk + 31) / 32;
+    const int rows = (!sequential && ctx->cfg.filtfilt_mode != 3 && est_tiles < static_cast<int64_t>(ctx->num_sms) * 4) ? kSmallRows : 32;
     int64_t chunks = 0, max_m = 0, tiles = 0;
     for (int i = 0; i < n; ++i) {
         const int64_t Lf = fix_off_host[i + 1] - fix_off_host[i];
@@ -913,7 +929,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
         tile_off[i] = static_cast<int>(tiles);
         const int64_t nc = sequential ? 1 : (M + kChunk - 1) / kChunk;
         chunks += nc;
-        tiles += (nc + 31) / 32;
+        tiles += (nc + rows - 1) / rows;
         if (chunks > 0x7fffffff) return set_error(ctx, SSFE_ERR_INVALID, "batch too large (chunks)");
     }
     chunk_off[n] = static_cast<int>(chunks);
@@ -953,6 +969,7 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     p.dith = out.dith;
     p.dith_raw = out.dith_raw ? 1 : 0;
     p.dith_f32 = out.dith_f32 ? 1 : 0;
+    p.rows = rows;
     p.dith_pf = 1;      // measured on the full corpus: backward final pass 6.00 ms without, 5.82 ms into L2, 5.82 ms into L1
     p.wavp = out.wavp;
     p.seg_off = out.seg_off_dev;
