@@ -309,14 +309,12 @@ __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const Rap
     __shared__ __align__(16) float s_xf[kCandWarps][4 * kXfStride];
     // candidates of the warp's four frames after the coarse stage: [4][20] peaks, [4][20] lags, [4] counts
     __shared__ __align__(16) float s_stash[kCandWarps][4 * kCMax + 4 * kCMax + 4];
+    __shared__ int s_fr[kCandWarps][12];                              // per frame of the warp: see the per-frame phase
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float *xf = s_xf[w];
-    // aliases inside the window of frame 0 (per-frame phase) ...
-    float *cc = xf;                                                   // [kCcMax = 288] fine correlation
-    float *pk = xf + kCcMax;                                          // [kFinePk] peaks
-    int *lc = reinterpret_cast<int *>(xf + kCcMax + kFinePk);         // [kFinePk] lags
-    static_assert(kCcMax + 2 * kFinePk <= kXfStride, "per-frame buffers must fit the window of frame 0");
+    // per-frame phase: every frame's correlation array [kCcMax = 288] and peak lists [2 x kFinePk] alias its own window
+    static_assert(kCcMax + 2 * kFinePk <= kXfStride, "per-frame buffers must fit the frame's window");
 
     const int u = tile_map[blockIdx.x];
     const RaptUtt ut = p.utts[u];
@@ -618,76 +616,139 @@ __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const Rap
         __syncwarp();          // every lane is done with the windows of this group (frame 0's is overwritten below)
 
         // -- per frame: correlation array, peaks, pruning, local costs --------------------------------------
-        int fbase = 0;
-        for (int f = f_begin; f < f_end; ++f) {
-            const int ncand_c = st_n[f];
-            const int g = g_tile + w + kCandWarps * f;
-            const long long gf = ut.fr_off + g;
-            const bool mine = active && my_f == f && !is_ref;
-            const float engr_f = __shfl_sync(0xffffffffu, s2, fbase + ncand_c);
+        // The group's frames are finished TOGETHER, a quarter-warp per frame (frame f_begin + q for lanes 8 q .. 8 q + 7),
+        // each in its own window buffer (dead by now).  Taken one frame at a time by the whole warp, this phase was a
+        // fifth of the kernel's instructions - the same ~330 instructions four times over, most lanes idle: a frame
+        // has ~3 coarse candidates, ~25 lags to scan and 20 record slots to write.
+        {
+            const int q = lane >> 3, l8 = lane & 7;
+            const int fq = f_begin + q;
+            const bool has_f = fq < f_end;
+            const int fqc = has_f ? fq : f_begin;
+            int *fr = s_fr[w];                                       // [4][3]: min / max first lag, max correlation
+            if (l8 == 0) { fr[3 * q] = 1 << 30; fr[3 * q + 1] = -(1 << 30); fr[3 * q + 2] = 0; }
+            __syncwarp();
+            const bool item = active && !is_ref;
+            if (item) {
+                const int k = my_f - f_begin;
+                atomicMin(&fr[3 * k], my_st);
+                atomicMax(&fr[3 * k + 1], my_st);
+                atomicMax(&fr[3 * k + 2], static_cast<int>(__float_as_uint(vmax)));   // values are >= 0: integer order
+            }
+            int rb = 0, cmax = 0;                                    // my frame's first item lane; most candidates of a frame
+            for (int f = f_begin; f < f_end; ++f) {
+                if (f < fqc) rb += st_n[f] + 1;
+                cmax = max(cmax, st_n[f]);
+            }
+            const int ncand_c = st_n[fqc];
+            const float engr_q = __shfl_sync(0xffffffffu, s2, rb + ncand_c);
+            __syncwarp();
             // The fine correlation is non-zero only inside the 7-lag windows, so only the span of those
             // windows (plus one zero on either side, which the peak test reads) is cleared and scanned.
             int z_lo = 0, z_hi = 0;
-            {
-                const int mn = __reduce_min_sync(0xffffffffu, mine ? my_st : (1 << 30));
-                const int mx = __reduce_max_sync(0xffffffffu, mine ? my_st : -(1 << 30));
-                if (ncand_c > 0) {
-                    z_lo = max(mn - start0 - 1, 0);
-                    z_hi = min(mx - start0 + 7 + 1, nlags0);
-                }
+            if (ncand_c > 0) {
+                z_lo = max(fr[3 * q] - start0 - 1, 0);
+                z_hi = min(fr[3 * q + 1] - start0 + 7 + 1, nlags0);
             }
-            float maxval = 0.0f;
-            int ncand = 0;
-            if (engr_f > 0.0f) {
-                for (int t = z_lo + lane; t < z_hi; t += 32) cc[t] = 0.0f;
-                __syncwarp();
-                // windows are written in candidate order; later ones overwrite earlier ones
-                for (int c = 0; c < ncand_c; ++c) {
-                    if (mine && my_c == c) {
-                        const int o = my_st - start0;
-#pragma unroll
-                        for (int t = 0; t < 7; ++t)
-                            if (o + t < kCcMax) cc[o + t] = dot[t];
-                    }
-                    __syncwarp();
-                }
-                // max over every value computed (order independent; all values are >= 0 after the fmaxf with 0)
-                maxval = __uint_as_float(__reduce_max_sync(0xffffffffu, mine ? __float_as_uint(vmax) : 0u));
-                ncand = pick_candidates<kFinePk>(cc, nlags0, start0, maxval, pk, lc, lane, z_lo + 1, z_hi - 1);
-            }
-            ncand = prune_candidates(pk, lc, ncand, lane);
-
-            // local costs (A5) and the value each candidate would emit (A8)
-            const float lagwt = cf.lagwt;
-            short *oloc = p.loc + gf * kCMax;
-            float *omp = p.mp + gf * kCMax, *of0 = p.f0c + gf * kCMax;
-            if (lane < ncand) {
-                const int loc1 = lc[lane];
-                const float pv = pk[lane];
-                float ftemp = 1.0 - (static_cast<float>(loc1) * lagwt);
-                omp[lane] = 1.0 - (pv * ftemp);
-                oloc[lane] = static_cast<short>(loc1);
-                ftemp = loc1;
-                if (loc1 > cf.start && loc1 < cf.stop) {
-                    const int jj = loc1 - cf.start;
-                    const float cormax = cc[jj], cprev = cc[jj + 1], cnext = cc[jj - 1];
-                    const float den = (2.0 * (cprev + cnext - (2.0 * cormax)));
-                    if (fabs(den) > 0.000001)
-                        ftemp += 2.0 - ((((5.0 * cprev) + (3.0 * cnext) - (8.0 * cormax)) / den));
-                }
-                of0[lane] = 16000.0 / ftemp;
-            } else if (lane == ncand) {
-                oloc[lane] = -1;
-                omp[lane] = c_rapt.vbias + maxval;
-                of0[lane] = 0.0f;
-            } else if (lane < kCMax) {
-                oloc[lane] = -1;
-                omp[lane] = 0.0f;
-                of0[lane] = 0.0f;
-            }
-            if (lane == 0) p.ncand[gf] = static_cast<unsigned char>(ncand + 1);
+            const float maxval_r = __uint_as_float(static_cast<unsigned>(fr[3 * q + 2]));
+            const bool e_ok = has_f && engr_q > 0.0f;
+            float *ccq = xf + fqc * kXfStride;                       // [kCcMax] fine correlation of my frame
+            float *pkq = ccq + kCcMax;                               // [kFinePk] peaks
+            int *lcq = reinterpret_cast<int *>(ccq + kCcMax + kFinePk);   // [kFinePk] lags
+            if (e_ok)
+                for (int t = z_lo + l8; t < z_hi; t += 8) ccq[t] = 0.0f;
             __syncwarp();
-            fbase += ncand_c + 1;
+            // windows are written in candidate order; later ones overwrite earlier ones
+            for (int c = 0; c < cmax; ++c) {
+                if (item && my_c == c && engr > 0.0f) {
+                    float *ccm = xf + my_f * kXfStride;
+                    const int o = my_st - start0;
+#pragma unroll
+                    for (int t = 0; t < 7; ++t)
+                        if (o + t < kCcMax) ccm[o + t] = dot[t];
+                }
+                __syncwarp();
+            }
+            // peaks above cand_thresh * maxval, in ascending lag order (get_cand), eight lags per step
+            const float maxval = e_ok ? maxval_r : 0.0f;
+            int ncand = 0;
+            {
+                const float clip = c_rapt.cand_thresh * maxval;
+                const int lastl = min(nlags0 - 2, z_hi - 1);
+                for (int base = max(1, z_lo + 1); __any_sync(0xffffffffu, e_ok && base < lastl); base += 8) {
+                    const int i = base + l8;
+                    bool ok = false;
+                    float qv = 0.0f;
+                    if (e_ok && i < lastl) {
+                        qv = ccq[i];
+                        ok = (qv > clip) && (qv >= ccq[i + 1]) && (qv >= ccq[i - 1]);
+                    }
+                    const unsigned m8 = (__ballot_sync(0xffffffffu, ok) >> (8 * q)) & 0xffu;
+                    const int pos = ncand + __popc(m8 & ((1u << l8) - 1u));
+                    if (ok && pos < kFinePk) {
+                        pkq[pos] = qv;
+                        lcq[pos] = i + start0;
+                    }
+                    ncand += __popc(m8);
+                }
+                ncand = min(ncand, kFinePk);
+            }
+            __syncwarp();
+            // keep the n_cands - 1 largest, by the original's partial bubble pass (order matters downstream)
+            if (__any_sync(0xffffffffu, ncand >= kCMax)) {
+                if (ncand >= kCMax && l8 == 0) {
+                    for (int outer = 0; outer < kCMax - 1; ++outer) {
+                        int idx = ncand - 1;
+                        for (int inner = ncand - 1 - outer; inner-- > 0; --idx) {
+                            const float sm = pkq[idx];
+                            if (sm > pkq[idx - 1]) {
+                                const int lt = lcq[idx];
+                                pkq[idx] = pkq[idx - 1];
+                                pkq[idx - 1] = sm;
+                                lcq[idx] = lcq[idx - 1];
+                                lcq[idx - 1] = lt;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (ncand >= kCMax) ncand = kCMax - 1;
+            }
+            // local costs (A5) and the value each candidate would emit (A8)
+            if (has_f) {
+                const long long gf = ut.fr_off + (g_tile + w + kCandWarps * fq);
+                const float lagwt = cf.lagwt;
+                short *oloc = p.loc + gf * kCMax;
+                float *omp = p.mp + gf * kCMax, *of0 = p.f0c + gf * kCMax;
+                for (int slot = l8; slot < kCMax; slot += 8) {
+                    if (slot < ncand) {
+                        const int loc1 = lcq[slot];
+                        const float pv = pkq[slot];
+                        float ftemp = 1.0 - (static_cast<float>(loc1) * lagwt);
+                        omp[slot] = 1.0 - (pv * ftemp);
+                        oloc[slot] = static_cast<short>(loc1);
+                        ftemp = loc1;
+                        if (loc1 > cf.start && loc1 < cf.stop) {
+                            const int jj = loc1 - cf.start;
+                            const float cormax = ccq[jj], cprev = ccq[jj + 1], cnext = ccq[jj - 1];
+                            const float den = (2.0 * (cprev + cnext - (2.0 * cormax)));
+                            if (fabs(den) > 0.000001)
+                                ftemp += 2.0 - ((((5.0 * cprev) + (3.0 * cnext) - (8.0 * cormax)) / den));
+                        }
+                        of0[slot] = 16000.0 / ftemp;
+                    } else if (slot == ncand) {
+                        oloc[slot] = -1;
+                        omp[slot] = c_rapt.vbias + maxval;
+                        of0[slot] = 0.0f;
+                    } else {
+                        oloc[slot] = -1;
+                        omp[slot] = 0.0f;
+                        of0[slot] = 0.0f;
+                    }
+                }
+                if (l8 == 0) p.ncand[gf] = static_cast<unsigned char>(ncand + 1);
+            }
+            __syncwarp();
         }
         f_begin = f_end;
     }
