@@ -893,11 +893,18 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
             return d;
         };
         p2 E[11], O[11], A[10];
+        // An odd-aligned pair is two halves of its even-aligned neighbours.  Left as a plain repacking, ptxas does not
+        // keep the eleven O pairs in registers: it rebuilds one (two MOVs into a scratch pair) for every use, ten
+        // uses per double step - 160 of the loop's 761 instructions were MOVs.  Passing the repacked pair through a
+        // multiply by a 1.0 the compiler cannot see (exact) makes it a value worth keeping: one FMUL2 and two MOVs
+        // per double step instead.
+        const p2 one2 = p2pack(c_rapt.one, c_rapt.one);
+        auto odd_pair = [&](p2 lo_src, p2 hi_src) -> p2 { return p2mul(p2pack(p2hi(lo_src), p2lo(hi_src)), one2); };
 #pragma unroll
         for (int t = 0; t < 11; ++t) E[t] = produce2(2 * t);
 #pragma unroll
         for (int t = 0; t < 10; ++t) {
-            O[t] = p2pack(p2hi(E[t]), p2lo(E[t + 1]));
+            O[t] = odd_pair(E[t], E[t + 1]);
             A[t] = p2pack(0.0f, 0.0f);
         }
         O[10] = p2pack(0.0f, 0.0f);
@@ -912,7 +919,7 @@ __global__ void __launch_bounds__(2 * kStatFrames) rapt_stat_kernel(const RaptPa
 #pragma unroll
                 for (int t = 0; t < 10; ++t) A[t] = p2add(A[t], p2mul(d1, O[(st + t) % 11]));
                 const p2 nw = produce2(22 * jb + 2 * st + 22);
-                O[(st + 10) % 11] = p2pack(p2hi(E[(st + 10) % 11]), p2lo(nw));
+                O[(st + 10) % 11] = odd_pair(E[(st + 10) % 11], nw);
                 E[st] = nw;
             }
         }
