@@ -355,6 +355,14 @@ def test_extract_large_corpus_properties(fe):
             assert torch.equal(res["bins"][pfo[k]:pfo[k + 1]], whole["bins"][fo[i]:fo[i + 1]]), i
         pos += len(part)
 
+    # a few utterances alone: a batch that cannot fill the GPU takes filter tiles of 8 chunks instead of 32 and the
+    # single-round paths of the carry scan and the dot-product local passes - the bits must not notice
+    for i in (0, 1234, 5599):
+        one = run(np.array([i]))
+        assert torch.equal(one["mel"], whole["mel"][fo[i]:fo[i + 1]]), i
+        assert torch.equal(one["f0_norm"], whole["f0_norm"][fo[i]:fo[i + 1]]), i
+        assert torch.equal(one["bins"], whole["bins"][fo[i]:fo[i + 1]]), i
+
     # host entry point == device entry point
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     host = fe.extract_host(torch.cat(pcm).cpu(), off, lo, hi, seed, skips)
