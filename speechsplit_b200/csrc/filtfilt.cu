@@ -485,6 +485,10 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
 // plain loads per lane and group: 2 KB in flight per warp only between the reductions - 2.4 / 2.1 ms, 1.7 TB/s.)
 // Groups that touch the odd extension, the appended sample or the ragged end of an utterance (two of ~47 for a 3 s
 // utterance) take their samples element by element.
+// A bulk copy starts at the 16-byte line of the group's first sample and ends with the line of its last one: up to
+// 14 bytes before and after the run.  Both lines hold samples of the same buffer (the caller's PCM array, whose
+// first utterance's first group is never a TMA group; the y1 workspace, allocated with 16 bytes to spare), so the
+// copy never leaves the allocation it reads.
 __device__ double g_filt_taps[5 * kChunk];      // [k][i], see ssfe_filt_cascade_taps
 constexpr int kDotWarps = 4;
 constexpr int kDotGroup = 4;                    // chunks per group / reduction
@@ -935,7 +939,8 @@ int filtfilt_run(ssfe_ctx *ctx, const void *x_dev, int dtype, const int64_t *in_
     chunk_off[n] = static_cast<int>(chunks);
     tile_off[n] = static_cast<int>(tiles);
     const int64_t ext_total = fix_off_host[n] + static_cast<int64_t>(n) * 2 * kPadLen;
-    int rc = ensure(ctx, ctx->ws.y1, ext_total * (sequential ? sizeof(double) : sizeof(float)));
+    // (+16: filt_dot_kernel's bulk copies run to the end of the 16-byte line their last sample lies in)
+    int rc = ensure(ctx, ctx->ws.y1, ext_total * (sequential ? sizeof(double) : sizeof(float)) + 16);
     if (rc) return rc;
     rc = ensure(ctx, ctx->ws.carry, 2 * chunks * 5 * sizeof(double));
     if (rc) return rc;
