@@ -279,11 +279,18 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
     // recurrence of sub-tile s runs, so the ~1-2 us of DRAM latency hide behind ~2000 cycles of fp64.
     using RawT = typename RawType<DTYPE, PASS>::T;
     RawT raw[ROWS];
-    auto is_fast = [&](int sub) -> bool {
+    // 2: every row present and every row segment inside the signal; 1: the same for the rows the tile has (an
+    // utterance's last tile is ragged: 28 of 32 rows for 3 s - a sixth of all tiles, and taking them down the
+    // element-wise path cost 2.5x the instructions of a plain sub-tile: 28 % of the forward final pass); 0: a sub-tile
+    // that touches the odd extension, the appended sample or the end of the signal.
+    auto is_fast = [&](int sub) -> int {
         const int js = jt + sub * kTileW;
-        if (rows != ROWS) return false;
-        if (PASS == 0) return (js >= kPadLen) && (js + (ROWS - 1) * kChunk + kTileW <= kPadLen + L);
-        return js + (ROWS - 1) * kChunk + kTileW <= M;
+        bool inside;
+        if (PASS == 0) inside = (js >= kPadLen) && (js + (rows - 1) * kChunk + kTileW <= kPadLen + L);
+        else inside = js + (rows - 1) * kChunk + kTileW <= M;
+        // (the backward final pass keeps its ragged tiles on the element-wise path: with the partial branch it ran at
+        // 6.29 instead of 5.84 ms - it sits at its 128-register limit - while the forward final pass went 4.14 -> 3.83)
+        return !inside ? 0 : (rows == ROWS ? 2 : (PASS == 0 ? 1 : 0));
     };
     // Edge tiles (the first tile of an utterance touches the 18 reflected samples, the last one is
     // ragged) are a third of all tiles for 3 s utterances, so they get the same treatment: every
@@ -295,20 +302,24 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
         else if (j >= kPadLen + Lf) nn = Lf - 2 - (j - kPadLen - Lf);
         return nn;
     };
-    auto issue = [&](int sub, bool fast_path) {
+    auto issue = [&](int sub, int fast_path) {
         const int js = jt + sub * kTileW;
         if (PASS == 0) {
-            if (fast_path) {
+            if (fast_path == 2) {
                 const RawT *xs = static_cast<const RawT *>(p.x) + (xbase + (js - kPadLen) + lane);
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) raw[r] = xs[r * kChunk];
+            } else if (fast_path == 1) {
+                const RawT *xs = static_cast<const RawT *>(p.x) + (xbase + (js - kPadLen) + lane);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) raw[r] = (r < rows) ? xs[r * kChunk] : RawT(0);
             } else {
                 const RawT *xs = static_cast<const RawT *>(p.x) + xbase;
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) raw[r] = xs[min(max(src_index(js + r * kChunk + lane), 0), L - 1)];
             }
         } else {
-            if (fast_path) {
+            if (fast_path == 2) {
                 const float *ys = y1 + (M - 1 - js - lane);          // reversed: row r is kChunk samples earlier
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) raw[r] = ys[-r * kChunk];
@@ -344,8 +355,8 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
     prefetch_dither(jt);
     for (int sub = 0; sub < kChunk / kTileW; ++sub) {
         const int jsub = jt + sub * kTileW;
-        const bool fast = is_fast(sub);
-        if (fast) {
+        const int fast = is_fast(sub);
+        if (fast) {                                  // (absent rows of a ragged tile were fetched as zeros)
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 double v = static_cast<double>(raw[r]);
@@ -386,15 +397,19 @@ __global__ void __launch_bounds__(kFiltWarps * 32, ((PASS == 0 || !FINAL) ? 5 : 
         __syncwarp();
         // ---- store (final passes): row-wise again ---------------------------------------------------
         if (FINAL) {
-            bool fast_out = fast;
+            int fast_out = fast;
             if (PASS == 1) {
-                // all 32 row segments map to output samples (none in the 18-sample pads)
-                const int n_hi = M - 1 - kPadLen - jsub, n_lo = n_hi - (ROWS - 1) * kChunk - (kTileW - 1);
-                fast_out = fast && n_lo >= 0 && n_hi < Lf && dith && wavp && !p.y && !p.wav && !p.wav64;
+                // all row segments map to output samples (none in the 18-sample pads)
+                const int n_hi = M - 1 - kPadLen - jsub, n_lo = n_hi - (rows - 1) * kChunk - (kTileW - 1);
+                if (!(n_lo >= 0 && n_hi < Lf && dith && wavp && !p.y && !p.wav && !p.wav64)) fast_out = 0;
             }
-            if (fast_out && PASS == 0) {
+            if (fast_out == 2 && PASS == 0) {
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) y1o[jsub + r * kChunk + lane] = static_cast<float>(tl[r * kTileStride + lane]);
+            } else if (fast_out == 1 && PASS == 0) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    if (r < rows) y1o[jsub + r * kChunk + lane] = static_cast<float>(tl[r * kTileStride + lane]);
             } else if (fast_out) {
                 // production path of the backward pass: wav = y * 0.96 + (U - 0.5) * 1e-06 -> f32 segment; the
                 // dither arrives as one raw generator word per sample (mt_walk_kernel<true>), tempering and the
