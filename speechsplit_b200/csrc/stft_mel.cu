@@ -40,6 +40,7 @@ constexpr int kStftThreads = kStftWarps * 32;
 constexpr int kPairFloats = kNfft + kHop;                   // 1280 samples = 5120 B per frame pair
 constexpr int kWarpTrans = 32 * kTransStride;               // float2 per warp
 constexpr int kMaxGroups = 16;
+constexpr int kTwBatch = 8;                                 // inter-pass twiddles fetched per batch
 constexpr int kMelFlush = 1 << 15;                          // mel_k flag: the lane's band ends with this group
 
 struct PairInfo {            // 16 bytes, built on the device once per launch
@@ -177,15 +178,26 @@ __global__ void __launch_bounds__(kStftThreads, 1) stft_mel_kernel(const StftPar
         // inter-pass twiddles W_1024^(lane k1) from the [k1][lane] table.  (Building them from five
         // table reads by complex products was measured: -52 shared-memory wavefronts per pair but +100
         // FP32 instructions made the kernel 7 % slower - issue and shared memory are balanced here.)
+        // (taken kTwBatch at a time, loads first, the compiler kept from mixing them: with one load right in front of its
+        // multiply the warp waited for shared memory on every twiddle - 17 % of the kernel's stall samples sat on the
+        // multiply.  9.20 -> 8.87 ms at 8 or 16 per batch, 9.10 at 4; the same treatment of the window loads changed
+        // nothing and a one-group prefetch in the mel loop cost 0.1 ms)
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const int k1 = bitrev5(r);
-            float2 y = v[r];
-            if (k1 != 0) {
-                const float2 t = s_tw[k1 * 32 + lane];
-                y = make_float2(v[r].x * t.x - v[r].y * t.y, v[r].x * t.y + v[r].y * t.x);
+        for (int r0 = 0; r0 < 32; r0 += kTwBatch) {
+            float2 t[kTwBatch];
+#pragma unroll
+            for (int q = 0; q < kTwBatch; ++q) {
+                const int k1 = bitrev5(r0 + q);
+                t[q] = (k1 != 0) ? s_tw[k1 * 32 + lane] : make_float2(1.0f, 0.0f);
             }
-            trans[lane * kTransStride + k1] = y;
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < kTwBatch; ++q) {
+                const int r = r0 + q, k1 = bitrev5(r);
+                float2 y = v[r];
+                if (k1 != 0) y = make_float2(v[r].x * t[q].x - v[r].y * t[q].y, v[r].x * t[q].y + v[r].y * t[q].x);
+                trans[lane * kTransStride + k1] = y;
+            }
         }
         __syncwarp();
 #pragma unroll
