@@ -1111,11 +1111,17 @@ __global__ void __launch_bounds__(kDpWarps * 32) rapt_dp_kernel(const RaptParams
                 store_block();
                 load_block((g >> 4) + 1);
             }
+            // (the record is read unconditionally and masked afterwards: a load guarded by the candidate count waits
+            // for the count's own trip to shared memory first - one more latency on every frame of the chain)
+            const int lcl = min(lane, kCMax - 1);
             const int ncand = bnc[fi];
-            const int loc = (lane < ncand) ? bloc[fi * kCMax + lane] : -1;
-            const float mp = (lane < ncand) ? bmp[fi * kCMax + lane] : 0.0f;
+            const int loc_r = bloc[fi * kCMax + lcl];
+            const float mp_r = bmp[fi * kCMax + lcl];
+            const double lg_r = blg[(fi + 1) * kCMax + lcl];
             const float v_from_uv = bsr[fi], uv_from_v = bsr[kDpBlk + fi];
-            const double lg = (lane < ncand) ? blg[(fi + 1) * kCMax + lane] : 0.0;
+            const int loc = (lane < ncand) ? loc_r : -1;
+            const float mp = (lane < ncand) ? mp_r : 0.0f;
+            const double lg = (lane < ncand) ? lg_r : 0.0;
             const double *lg_row = blg + fi * kCMax;             // the previous frame's
             float errmin = FLT_MAX;
             int minloc = 0;
