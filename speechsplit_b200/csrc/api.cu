@@ -258,6 +258,16 @@ extern "C" int ssfe_create(ssfe_ctx **out, int device, const ssfe_config *cfg)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_dith_free, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
         if ((e = cudaEventCreateWithFlags(&ctx->ev_mt_go, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        {
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            const char *v = getenv("SSFE_OH_PRIO");
+            const int pri = (v && atoi(v) == 0) ? 0 : hi_pri;
+            if ((e = cudaStreamCreateWithPriority(&ctx->aux2, cudaStreamNonBlocking, pri)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaStreamCreate"); break; }
+        }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_oh_go, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_oh_done, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaEventCreate"); break; }
+        if (const char *v = getenv("SSFE_ONEHOT_EARLY")) ctx->onehot_early = atoi(v);
         ctx->stream = ctx->own_stream;
         if ((rc = init_stft_tables(ctx))) break;
         if ((rc = init_filtfilt(ctx))) break;
@@ -307,7 +317,8 @@ extern "C" void ssfe_destroy(ssfe_ctx *ctx)
         for (cudaEvent_t e : row)
             if (e) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
-    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->aux_free[0], ctx->aux_free[1],
+    if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_dith_free, ctx->ev_mt_go, ctx->ev_oh_go, ctx->ev_oh_done, ctx->aux_free[0], ctx->aux_free[1],
                           ctx->ev_hd_ready[0], ctx->ev_hd_ready[1]})
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < ssfe_ctx::kHostSlots; ++i)
@@ -484,9 +495,21 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
         if ((rc = ensure(ctx, ctx->ws.rapt_f0, foff[n] * sizeof(float)))) return rc;
         f0_raw = static_cast<float *>(ctx->ws.rapt_f0.p);
     }
-    if ((rc = rapt_run(ctx, wavp, start.data(), len.data(), foff.data(), n, b->f0_lo, b->f0_hi, f0_raw))) return rc;
+    // The one-hot output is 257 floats per frame of which 256 are zero whatever the F0 turns out to be (8.4 GB for the
+    // bench corpus, 1.5 ms at HBM write speed): the zeros go out on a side stream beside the RAPT kernels, which are
+    // issue / FMA-pipe bound and leave HBM idle, and the normalisation kernel drops the ones in at the end.
+    ctx->oh_started = false;
+    ctx->oh_pending = (o->onehot && ctx->onehot_early > 0) ? o->onehot : nullptr;
+    ctx->oh_rows = foff[n];
+    rc = onehot_zero_fork(ctx, 1);
+    if (!rc) rc = rapt_run(ctx, wavp, start.data(), len.data(), foff.data(), n, b->f0_lo, b->f0_hi, f0_raw);
+    ctx->oh_pending = nullptr;
+    const bool oh_zeroed = ctx->oh_started;
     mark(ctx, ST_POST);
-    rc = f0_post_run(ctx, f0_raw, foff.data(), n, o->f0_norm, nullptr, o->onehot, o->bins, d_foff);
+    // (also when rapt_run failed: nothing of this call may still be writing the caller's buffer once its stream is idle)
+    if (oh_zeroed) SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_oh_done, 0));
+    if (rc) return rc;
+    rc = f0_post_run(ctx, f0_raw, foff.data(), n, o->f0_norm, nullptr, o->onehot, o->bins, d_foff, oh_zeroed);
     mark(ctx, ST_COUNT);
     return rc;
 }

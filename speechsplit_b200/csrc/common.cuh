@@ -49,6 +49,14 @@ struct ssfe_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // ssfe_extract_host pipeline
     cudaStream_t aux = nullptr;                               // the dither stream runs beside filtfilt
+    cudaStream_t aux2 = nullptr;                              // zero stream of the one-hot output, beside the RAPT kernels
+    cudaEvent_t ev_oh_go = nullptr, ev_oh_done = nullptr;
+    // where the zero stream starts: 0 = never (one-hot written in one piece at the end), 1 = before the RAPT kernels,
+    // 2 = beside rapt_cand, 3 = beside rapt_stat, 4 = beside rapt_dp (SSFE_ONEHOT_EARLY, A/B hook)
+    int onehot_early = 2;
+    float *oh_pending = nullptr;                              // one-hot buffer of the current call while its zero stream has not started
+    int64_t oh_rows = 0;
+    bool oh_started = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     static constexpr int kHostSlots = 4;                      // device slots of ssfe_extract_host
     cudaEvent_t ev_h2d[kHostSlots] = {}, ev_comp[kHostSlots] = {}, ev_d2h[kHostSlots] = {};
@@ -210,8 +218,21 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host /* 
              const float *f0_lo, const float *f0_hi, float *f0_dev);
 
 // a7+a8 (+a9 when bins/onehot given) over a ragged batch; frame offsets are HOST [n+1]
+// onehot_zeroed: the one-hot buffer was already filled with zeros (onehot_zero_start, awaited by the caller):
+// only the ones are dropped in, by the normalisation kernel itself
 int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_host, int n,
                 float *f0_norm_dev, float *stats_dev, float *onehot, int64_t *bins,
-                const int64_t *frame_off_dev = nullptr);
+                const int64_t *frame_off_dev = nullptr, bool onehot_zeroed = false);
+// rows x 257 zeros into `onehot` on the side stream aux2, from where ctx->stream stands now; ctx->ev_oh_done is
+// recorded behind it.  Returns SSFE_OK with *started = false when the buffer is not 16-byte aligned.
+int onehot_zero_start(ssfe_ctx *ctx, float *onehot, int64_t rows, bool *started);
+// called by rapt_run at its fork points: starts the pending zero stream if `where` is the configured one
+inline int onehot_zero_fork(ssfe_ctx *ctx, int where)
+{
+    if (!ctx->oh_pending || ctx->onehot_early != where) return SSFE_OK;
+    float *buf = ctx->oh_pending;
+    ctx->oh_pending = nullptr;
+    return onehot_zero_start(ctx, buf, ctx->oh_rows, &ctx->oh_started);
+}
 
 }  // namespace ssfe

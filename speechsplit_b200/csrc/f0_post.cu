@@ -10,6 +10,7 @@
 //   collator: data_loader.py:101-128 (crop, clip [0,1], zero-pad to 192, F0 pad -1e10) feeding
 //       solver.py:160-163.
 #include "common.cuh"
+#include <cstdlib>
 #include <algorithm>
 
 namespace ssfe {
@@ -194,7 +195,8 @@ __device__ __forceinline__ long long quantize_value(double x, int num_bins, bool
 // per frame: speaker_normalization with the utterance's stats, then the bin of the stored f32 value
 __global__ void f0_norm_quant_kernel(const float *__restrict__ f0, const int64_t *__restrict__ frame_off,
                                      int n, const float *__restrict__ stats, int64_t total,
-                                     float *__restrict__ f0_norm, int64_t *__restrict__ bins)
+                                     float *__restrict__ f0_norm, int64_t *__restrict__ bins,
+                                     float *__restrict__ onehot_ones)
 {
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (t >= total) return;
@@ -210,10 +212,28 @@ __global__ void f0_norm_quant_kernel(const float *__restrict__ f0, const int64_t
         o = static_cast<float>(__ddiv_rn(__dadd_rn(z, 1.0), 2.0));                            // :40, saved f32
     }
     if (f0_norm) f0_norm[t] = o;
-    if (bins) {
+    if (bins || onehot_ones) {
         bool bad = false;
-        bins[t] = quantize_value(static_cast<double>(o), 256, &bad);
+        const long long b = quantize_value(static_cast<double>(o), 256, &bad);
+        if (bins) bins[t] = b;
+        if (onehot_ones) onehot_ones[t * 257 + b] = 1.0f;       // the row's zeros are already there (onehot_zero_start)
     }
+}
+
+// count float4 of zeros, grid-stride: the zero stream of the one-hot output.  A small persistent grid - it runs
+// beside the RAPT kernels and should take the HBM bandwidth they leave idle, not their SM slots.
+__global__ void __launch_bounds__(256) zero_stream_kernel(float4 *__restrict__ dst, int64_t count)
+{
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < count; i += 4 * stride) {
+        dst[i] = z;
+        dst[i + stride] = z;
+        dst[i + 2 * stride] = z;
+        dst[i + 3 * stride] = z;
+    }
+    for (; i < count; i += stride) dst[i] = z;
 }
 
 template <typename T>
@@ -331,7 +351,7 @@ static int64_t grid_for(int64_t work, int threads) { return (work + threads - 1)
 
 namespace ssfe {
 int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_host, int n, float *f0_norm_dev,
-                float *stats_dev, float *onehot, int64_t *bins, const int64_t *frame_off_dev)
+                float *stats_dev, float *onehot, int64_t *bins, const int64_t *frame_off_dev, bool onehot_zeroed)
 {
     const int64_t total = frame_off_host[n];
     if (n == 0 || total == 0) return SSFE_OK;
@@ -350,14 +370,35 @@ int f0_post_run(ssfe_ctx *ctx, const float *f0_dev, const int64_t *frame_off_hos
     }
     f0_stats_kernel<<<static_cast<unsigned>(grid_for(n, kStatsWarps)), kStatsWarps * 32, 0, ctx->stream>>>(f0_dev, d_off, n, scratch, stats);
     SSFE_LAUNCHED(ctx);
-    int64_t *use_bins = bins ? bins : (onehot ? tmp_bins : nullptr);
+    int64_t *use_bins = bins ? bins : ((onehot && !onehot_zeroed) ? tmp_bins : nullptr);
     f0_norm_quant_kernel<<<static_cast<unsigned>(grid_for(total, 256)), 256, 0, ctx->stream>>>(
-        f0_dev, d_off, n, stats, total, f0_norm_dev, use_bins);
+        f0_dev, d_off, n, stats, total, f0_norm_dev, use_bins, (onehot && onehot_zeroed) ? onehot : nullptr);
     SSFE_LAUNCHED(ctx);
-    if (onehot) {
+    if (onehot && !onehot_zeroed) {
         launch_onehot<int64_t>(ctx->stream, use_bins, total, 257, onehot);
         SSFE_LAUNCHED(ctx);
     }
+    return SSFE_OK;
+}
+
+int onehot_zero_start(ssfe_ctx *ctx, float *onehot, int64_t rows, bool *started)
+{
+    *started = false;
+    const int64_t total = rows * 257;
+    if (total == 0 || (reinterpret_cast<uintptr_t>(onehot) & 15) != 0) return SSFE_OK;
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_oh_go, ctx->stream));       // not ahead of anything queued before this call
+    SSFE_CUDA(ctx, cudaStreamWaitEvent(ctx->aux2, ctx->ev_oh_go, 0));
+    const int64_t n4 = total / 4;
+    if (n4 > 0) {
+        static const int ctas = getenv("SSFE_OH_GRID") ? atoi(getenv("SSFE_OH_GRID")) : 32;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n4 + 1023) / 1024, ctas));
+        zero_stream_kernel<<<grid, 256, 0, ctx->aux2>>>(reinterpret_cast<float4 *>(onehot), n4);
+        SSFE_LAUNCHED(ctx);
+    }
+    if (total > 4 * n4)                                                // the last one to three floats
+        SSFE_CUDA(ctx, cudaMemsetAsync(onehot + 4 * n4, 0, (total - 4 * n4) * sizeof(float), ctx->aux2));
+    SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_oh_done, ctx->aux2));
+    *started = true;
     return SSFE_OK;
 }
 }  // namespace ssfe

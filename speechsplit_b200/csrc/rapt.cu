@@ -1498,6 +1498,9 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
     rapt_decimate_kernel<<<static_cast<unsigned>(dsn / kDecTile), kDecThreads, 0, st>>>(p, dec_map);
     SSFE_LAUNCHED(ctx);
     mark(ctx, ST_RAPT_CAND);
+    // the zero stream of the one-hot output starts here by default (extract_device): beside the candidate kernel,
+    // which leaves HBM idle - beside the decimation kernel it cost that kernel what it saved at the end
+    if ((rc = onehot_zero_fork(ctx, 2))) return rc;
     if (fr > 0) {
         rapt_cand_kernel<<<static_cast<unsigned>(cand_tiles), kCandWarps * 32, 0, st>>>(p, d_cand_tiles, cand_map);
         SSFE_LAUNCHED(ctx);
@@ -1505,6 +1508,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         // the next call's dither generation (side stream, high priority) may start here, beside the stationarity
         // kernel (extract_device has the measurements)
         if (!ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
+        if ((rc = onehot_zero_fork(ctx, 3))) return rc;
         rapt_stat_kernel<<<static_cast<unsigned>(stat_tiles), 2 * kStatFrames, kStatSmem, st>>>(p, d_stat_tiles, stat_map);
         SSFE_LAUNCHED(ctx);
     } else {
@@ -1512,6 +1516,7 @@ int rapt_run(ssfe_ctx *ctx, const float *wav_base, const int64_t *start_host, co
         if (!ctx->mt_go_at_start) SSFE_CUDA(ctx, cudaEventRecord(ctx->ev_mt_go, st));
     }
     mark(ctx, ST_RAPT_DP);
+    if ((rc = onehot_zero_fork(ctx, 3)) || (rc = onehot_zero_fork(ctx, 4))) return rc;
     rapt_dp_kernel<<<static_cast<unsigned>((n + kDpWarps - 1) / kDpWarps), kDpWarps * 32, 0, st>>>(p);
     SSFE_LAUNCHED(ctx);
     return SSFE_OK;

@@ -48,6 +48,14 @@ def _extract(fe, pcm, meta, want, dtype=torch.int16):
     return fe.extract(x, off, lo, hi, seed, skip, want=want)
 
 
+def _extract_out(fe, pcm, meta, want, out):
+    off = np.concatenate([[0], np.cumsum([len(p) for p in pcm])]).astype(np.int64)
+    x = torch.from_numpy(np.concatenate(pcm))
+    lo = [50.0 if m["gender"] == "M" else 100.0 for m in meta]
+    hi = [250.0 if m["gender"] == "M" else 600.0 for m in meta]
+    return fe.extract(x, off, lo, hi, [int(m["spk"][1:]) for m in meta], [m["skip"] for m in meta], want=want, out=out)
+
+
 def _check_against(res, meta, exact_f0):
     fo, fx = res["frame_offsets"], res["fixed_offsets"]
     mel = res["mel"].cpu().numpy()
@@ -156,6 +164,37 @@ def test_extract_batch_order_and_split_invariance(fe, golden_dir):
         one = _extract(fe, [pcm[i]], [meta[i]], ("mel", "f0_norm", "bins"))
         for name in ("mel", "f0_norm", "bins"):
             assert torch.equal(one[name], full[name][fo[i]:fo[i + 1]]), (name, i)
+
+
+def test_extract_onehot_zero_stream_paths(fe, golden_dir, monkeypatch):
+    """The one-hot rows are written as a zero stream on a side stream beside the RAPT kernels plus one 1.0 per
+    row from the normalisation kernel (ssfe_extract, api.cu).  That path, the single-kernel path it replaced
+    (SSFE_ONEHOT_EARLY=0) and the fallback for a buffer that is not 16-byte aligned must give the same bits,
+    whatever the buffer held before, for row counts of every residue mod 4."""
+    from speechsplit_b200 import FrontEnd
+    pcm, meta = _golden_batch(golden_dir, NAMES)
+    monkeypatch.setenv("SSFE_ONEHOT_EARLY", "0")
+    late = FrontEnd(0)
+    monkeypatch.delenv("SSFE_ONEHOT_EARLY")
+    try:
+        seen = set()
+        for k in range(1, len(pcm) + 1):
+            ref = _extract(late, pcm[:k], meta[:k], ("mel", "f0_norm", "bins", "onehot"))
+            T = int(ref["frame_offsets"][-1])
+            seen.add(T % 4)
+            assert torch.equal(ref["onehot"].argmax(1), ref["bins"]) and bool((ref["onehot"].sum(1) == 1).all())
+            for shift in (0, 1):            # shift 1: rows start 4 bytes off a 16-byte boundary
+                buf = torch.full((T * 257 + 4,), 7.0, dtype=torch.float32, device=ref["onehot"].device)
+                oh = buf[shift:shift + T * 257].view(T, 257)
+                for _ in range(2):          # twice: the second call finds the first call's ones in the buffer
+                    got = _extract_out(fe, pcm[:k], meta[:k], ("mel", "f0_norm", "bins", "onehot"), dict(onehot=oh))
+                    assert got["onehot"].data_ptr() == oh.data_ptr()
+                    for name in ("mel", "f0_norm", "bins", "onehot"):
+                        assert torch.equal(got[name], ref[name]), (name, k, shift)
+                assert bool((buf[:shift] == 7.0).all()) and bool((buf[shift + T * 257:] == 7.0).all())
+        assert len(seen) >= 2
+    finally:
+        late.close()
 
 
 def test_extract_host_matches_device_path(fe, golden_dir):
