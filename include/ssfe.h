@@ -18,7 +18,9 @@
  *   - a ragged batch is the concatenation of its utterances plus an offsets array [n+1].
  *   - one context per GPU; a context is not thread-safe, different contexts are independent.
  *   - all work is enqueued on the context's stream (ssfe_set_stream); calls are asynchronous
- *     unless stated otherwise.  There is NO CPU fallback: without a CUDA device ssfe_create fails.
+ *     unless stated otherwise.  (Internal side streams - the dither generator, the zero stream of
+ *     the one-hot output - are forked from that stream and joined back to it by events: whatever
+ *     the caller orders against the context's stream is ordered against all of a call's work.)  There is NO CPU fallback: without a CUDA device ssfe_create fails.
  */
 #ifndef SSFE_H_
 #define SSFE_H_
