@@ -302,6 +302,14 @@ constexpr int kCandTile = 16;      // frames per CTA (4 per warp)
 constexpr int kXfStride = 456;     // >= ncomp (441), = 8 mod 32, multiple of 4
 constexpr int kFinePk = 84;        // peaks of the fine correlation: it is non-zero on <= 20 x 7 lags, so <= 70
 
+// float(num / sqrt(prod)) in double, out of line: the double-precision division and square root expand to ~50
+// instructions each, and rapt_cand_kernel holds eleven copies of the pair when they are inlined into its unrolled
+// normalisation loops (its 59 KB of SASS miss the instruction cache: 12 % of its stall samples are no_instructions)
+__device__ __noinline__ float nccf_norm(float num, double prod)
+{
+    return static_cast<float>(static_cast<double>(num) / sqrt(prod));
+}
+
 __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const RaptParams p, const int *__restrict__ tile_off,
                                                                     const int *__restrict__ tile_map)
 {
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const Rap
         __syncwarp();
         float tmax = 0.0f;
         for (int lag = l8; lag < nlags; lag += 8) {
-            const float t = pos_e ? static_cast<float>(ccc[lag] / sqrt(cec[lag] * engr)) : 0.0f;
+            const float t = pos_e ? nccf_norm(ccc[lag], cec[lag] * engr) : 0.0f;
             ccc[lag] = t;
             tmax = fmaxf(tmax, t);
         }
@@ -606,7 +614,7 @@ __global__ void __launch_bounds__(kCandWarps * 32, 6) rapt_cand_kernel(const Rap
 #pragma unroll
             for (int t = 0; t < 7; ++t) {
                 if (engc < 1.0) engc = 1.0;
-                const float v = static_cast<float>(dot[t] / sqrt(10000.0 + (engc * engr)));
+                const float v = nccf_norm(dot[t], 10000.0 + (engc * engr));
                 dot[t] = v;
                 vmax = fmaxf(vmax, v);
                 const float a0 = xs[t], az = xs[t + kWin];
