@@ -496,8 +496,10 @@ int extract_device(ssfe_ctx *ctx, const ssfe_batch *b, const void *x_dev, int dt
         f0_raw = static_cast<float *>(ctx->ws.rapt_f0.p);
     }
     // The one-hot output is 257 floats per frame of which 256 are zero whatever the F0 turns out to be (8.4 GB for the
-    // bench corpus, 1.5 ms at HBM write speed): the zeros go out on a side stream beside the RAPT kernels, which are
-    // issue / FMA-pipe bound and leave HBM idle, and the normalisation kernel drops the ones in at the end.
+    // bench corpus, 1.5 ms at HBM write speed at the very end of the call): the zeros go out on a side stream beside
+    // rapt_cand (rapt_run forks it) and the normalisation kernel drops the ones in at the end.  The overlap is far from
+    // free - a full-width zero stream costs the kernel it meets ~1.1 ms, a 32-CTA one at high priority 0.8 ms - so
+    // the call gains ~0.5 ms of the 1.2 (measurements in DESIGN.md 4.5; SSFE_ONEHOT_EARLY=0 restores the single kernel).
     ctx->oh_started = false;
     ctx->oh_pending = (o->onehot && ctx->onehot_early > 0) ? o->onehot : nullptr;
     ctx->oh_rows = foff[n];
