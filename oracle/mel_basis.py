@@ -9,6 +9,10 @@ restates the published algorithm of that version range: Slaney mel scale (htk=Fa
 Slaney area normalisation (norm=1 / 'slaney'), float32 storage.
 Cross-checks available in-container: torchaudio.functional.melscale_fbanks(...,'slaney','slaney') and
 transformers.audio_utils.mel_filter_bank(norm='slaney', mel_scale='slaney') (tests/test_oracle.py).
+Corroboration (not a pin): evaluated at other parameters the same code reproduces published outputs of the real
+librosa.filters.mel - the first entries of Whisper's mel_filters.npz (sr 16000, n_fft 400, 80 filters) to all
+eight printed digits, sign of the zero at [0, 0] included, and librosa's docstring example - quoted from memory
+(tests/test_oracle.py::test_mel_restatement_reproduces_published_librosa_outputs).
 """
 import numpy as np
 

@@ -85,6 +85,27 @@ def test_mel_basis_vs_transformers():
     assert np.abs(w.view(np.int32) - t.view(np.int32)).max() <= 1
 
 
+def test_mel_restatement_reproduces_published_librosa_outputs():
+    """Two outputs of the real ``librosa.filters.mel`` that are public, evaluated with the restatement at THEIR
+    parameters (the function is the same one, only sr / n_fft / fmin / fmax / n_mels differ from the reference's call):
+
+    * OpenAI Whisper ships ``mel_filters.npz`` = ``librosa.filters.mel(sr=16000, n_fft=400, n_mels=80)`` (so its
+      audio.py says); its widely printed first entries are ``-0., 0.02486259`` in filter 0 and ``0.00199082,
+      0.02287177`` at the start of filter 1;
+    * librosa's own docstring example ``librosa.filters.mel(sr=22050, n_fft=2048)`` prints ``[0., 0.016, ...]``.
+
+    PROVENANCE: neither file is in this image - the numbers are quoted from memory of those public artefacts, which
+    makes this a corroboration of the restated formulae (mel scale break, area normalisation, f32 storage, even the
+    negative zero at [0, 0]), not the pin that tests/test_oracle_thirdparty.py becomes on a box with librosa."""
+    w = mel_filterbank(16000, 400, 80, 0.0, 8000.0)
+    assert w.shape == (80, 201) and w.dtype == np.float32
+    assert w[0, 0] == 0.0 and np.signbit(w[0, 0])
+    assert abs(float(w[0, 1]) - 0.02486259) < 5e-9 and w[0, 2] == 0.0
+    assert abs(float(w[1, 1]) - 0.00199082) < 5e-9 and abs(float(w[1, 2]) - 0.02287177) < 5e-9
+    d = mel_filterbank(22050, 2048, 128, 0.0, 11025.0)
+    assert d.shape == (128, 1025) and d[0, 0] == 0.0 and round(float(d[0, 1]), 3) == 0.016
+
+
 @pytest.mark.parametrize("name", ["pipeline_p226.npz", "pipeline_p225.npz"])
 def test_pipeline_matches_reference(golden_dir, name):
     """make_spect_f0.py:47-74 through the oracle == through the reference's own functions."""
