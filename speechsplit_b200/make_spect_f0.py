@@ -11,21 +11,85 @@ with ``np.save(..., allow_pickle=False)``.  The per-utterance loop body (:50-67)
 reference's ``soundfile`` is used when importable).
 """
 import argparse
+import io
 import os
 import pickle
+import struct
 import time
 import wave
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
+from numpy.lib import format as npy_format
 
 from .frontend import GENDER_RANGE, default_frontend
 from .sharding import fixed_length
 
 
+def read_wav_pcm16(path):
+    """Fast path of read_wav: a RIFF/WAVE file holding mono 16-bit PCM (format tag 1, or WAVE_FORMAT_EXTENSIBLE
+    with the PCM sub-format) -> (read-only int16 array, fs); None for anything else.  One read of the whole file
+    and a walk over its chunk headers: 32 us per 3 s file against 116 us through the stdlib ``wave`` module
+    (profiles/microbench/wav_npy_io.py) - in the script form the WAV reads were 1.0 s of a 1.4 s run."""
+    with open(path, "rb") as fh:
+        b = fh.read()
+    nb = len(b)
+    if nb < 12 or b[:4] != b"RIFF" or b[8:12] != b"WAVE":
+        return None
+    pos, fmt = 12, None
+    while pos + 8 <= nb:
+        cid = b[pos:pos + 4]
+        size = int.from_bytes(b[pos + 4:pos + 8], "little")
+        body = pos + 8
+        if cid == b"fmt ":
+            if size < 16 or body + 16 > nb:
+                return None
+            tag, nch, fs, _, align, bits = struct.unpack_from("<HHIIHH", b, body)
+            if tag == 0xFFFE and size >= 40 and body + 26 <= nb:       # extensible: the sub-format GUID starts with the tag
+                tag = struct.unpack_from("<H", b, body + 24)[0]
+            if tag != 1 or nch != 1 or bits != 16 or align != 2:
+                return None
+            fmt = fs
+        elif cid == b"data":
+            if fmt is None:
+                return None
+            n = min(size, nb - body) // 2                              # whole frames only, like wave.readframes
+            return np.frombuffer(b, dtype="<i2", count=n, offset=body), fmt
+        pos = body + size + (size & 1)                                 # chunks are word aligned
+    return None
+
+
+_NPY_HEADERS = {}
+
+
+def save_npy(path, arr):
+    """``np.save(path, arr, allow_pickle=False)`` for a C-contiguous numeric array, byte for byte (NPY v1.0, same header
+    padding - the header comes from numpy's own ``write_array_header_1_0``, cached per (shape, dtype)), without
+    np.save's per-call checks: 25 us per file against 48 (profiles/microbench/wav_npy_io.py).  make_spect_f0.py:71-74."""
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype.hasobject:
+        raise ValueError("save_npy: object arrays are not allowed (allow_pickle=False)")
+    key = (arr.shape, arr.dtype.str)
+    head = _NPY_HEADERS.get(key)
+    if head is None:
+        bio = io.BytesIO()
+        npy_format.write_array_header_1_0(bio, npy_format.header_data_from_array_1_0(arr))
+        head = bio.getvalue()
+        if len(_NPY_HEADERS) < 65536:
+            _NPY_HEADERS[key] = head
+    if not path.endswith(".npy"):
+        path = path + ".npy"                                           # np.save appends the extension
+    with open(path, "wb") as fh:
+        fh.write(head)
+        fh.write(arr.data)
+
+
 def read_wav(path):
     """-> (int16 or float64 array, fs).  16-bit PCM stays int16 (x = v/32768 exactly, like sf.read);
     any other sample format goes through soundfile as float64, as at make_spect_f0.py:50."""
+    got = read_wav_pcm16(path)
+    if got is not None:
+        return got
     try:
         import soundfile as sf
     except ImportError:
@@ -104,14 +168,18 @@ def extract_speakers(fe, speakers, max_utts_per_call=4096, stats=None):
 
 
 def make_spect_f0(root_dir="assets/wavs", target_dir="assets/spmel", target_dir_f0="assets/raptf0",
-                  spk2gen_path="assets/spk2gen.pkl", device=None, verbose=True, stats=None, io_threads=8):
+                  spk2gen_path="assets/spk2gen.pkl", device=None, verbose=True, stats=None, io_threads=1, frontend=None):
     """stats: optional dict that receives where the wall time went (read_s, pack_s, extract_s, write_s, files).
-    io_threads: WAV reads and NPY writes go through a thread pool (file I/O releases the GIL); measured on a
-    109 x 40 tree, one thread spends 0.35 s reading and 0.24 s writing around 0.12 s of GPU work."""
+    frontend: the FrontEnd to use (default: the process-wide one on ``device``; the CPU tests of the file handling pass a stub).
+    io_threads: > 1 sends WAV reads and NPY writes through a thread pool (for slow file systems; see below)."""
     spk2gen = pickle.load(open(spk2gen_path, "rb"))            # :19
-    pool = ThreadPoolExecutor(max_workers=max(1, int(io_threads)))
+    # io_threads <= 1: reads and writes inline.  A file costs 30-70 us to read and 25-40 us to write, less than a
+    # hand-over to a worker thread and back under the GIL: through an 8-thread pool the same tree took 2.07 s against
+    # 1.0 s inline (profiles/microbench/wav_npy_io.py, stub front end), so the pool is opt-in for slow file systems.
+    n_threads = max(1, int(io_threads))
+    pool = ThreadPoolExecutor(max_workers=n_threads) if n_threads > 1 else None
     pending = []
-    fe = default_frontend(device)
+    fe = frontend if frontend is not None else default_frontend(device)
     dir_name, subdirs, _ = next(os.walk(root_dir))             # :28
     if verbose:
         print("Found directory: %s" % dir_name)
@@ -127,7 +195,11 @@ def make_spect_f0(root_dir="assets/wavs", target_dir="assets/spmel", target_dir_
             _, _, files = next(os.walk(os.path.join(dir_name, subdir)))
             files = sorted(files)                              # :48
             t0 = time.perf_counter()
-            got = list(pool.map(lambda f: read_wav(os.path.join(dir_name, subdir, f)), files))
+            src = os.path.join(dir_name, subdir)
+            if pool is not None:
+                got = list(pool.map(lambda f: read_wav(os.path.join(src, f)), files))
+            else:
+                got = [read_wav(os.path.join(src, f)) for f in files]
             utts = []
             for x, fs in got:
                 assert fs == 16000                             # :51
@@ -137,15 +209,19 @@ def make_spect_f0(root_dir="assets/wavs", target_dir="assets/spmel", target_dir_
             names[subdir] = files
             yield subdir, spk2gen[subdir], utts
 
+    t0 = time.perf_counter()
     try:
         for spk, k, S, f0n in extract_speakers(fe, speakers(), stats=stats):
             stem = names[spk][k][:-4]
             t0 = time.perf_counter()
-            # the rows are views of the call's result arrays, which stay alive until the writes are done
-            pending.append(pool.submit(np.save, os.path.join(target_dir, spk, stem), S.astype(np.float32, copy=False),
-                                       allow_pickle=False))                                               # :71-72
-            pending.append(pool.submit(np.save, os.path.join(target_dir_f0, spk, stem), f0n.astype(np.float32, copy=False),
-                                       allow_pickle=False))                                               # :73-74
+            # (pool: the rows are views of the call's result arrays, which stay alive until the writes are done)
+            for path, arr in ((os.path.join(target_dir, spk, stem), S),                                      # :71-72
+                              (os.path.join(target_dir_f0, spk, stem), f0n)):                                # :73-74
+                arr = arr.astype(np.float32, copy=False)
+                if pool is not None:
+                    pending.append(pool.submit(save_npy, path, arr))
+                else:
+                    save_npy(path, arr)
             if stats is not None:
                 stats["write_s"] = stats.get("write_s", 0.0) + (time.perf_counter() - t0)
                 stats["files"] = stats.get("files", 0) + 1
@@ -153,7 +229,8 @@ def make_spect_f0(root_dir="assets/wavs", target_dir="assets/spmel", target_dir_
         for f in pending:
             f.result()                                             # re-raises an I/O error of a worker
     finally:
-        pool.shutdown(wait=True)
+        if pool is not None:
+            pool.shutdown(wait=True)
     if stats is not None:
         stats["write_s"] = stats.get("write_s", 0.0) + (time.perf_counter() - t0)
 

@@ -391,3 +391,117 @@ def test_read_wav_sample_formats(tmp_path):
     wavfile.write(tmp_path / "st.wav", 16000, np.stack([v16, v16], 1))
     with pytest.raises(ValueError):
         read_wav(str(tmp_path / "st.wav"))
+
+
+def _riff(chunks):
+    body = b"WAVE" + b"".join(cid + len(data).to_bytes(4, "little") + data + (b"\0" if len(data) & 1 else b"")
+                              for cid, data in chunks)
+    return b"RIFF" + len(body).to_bytes(4, "little") + body
+
+
+def test_read_wav_pcm16_fast_path(tmp_path):
+    """read_wav_pcm16 (one read + a walk over the chunk headers) against the stdlib reader, on the layouts real files
+    have: extra chunks before and after the data, odd-sized chunks and their pad byte, WAVE_FORMAT_EXTENSIBLE, a data
+    chunk that claims more than the file holds; everything that is not mono 16-bit PCM is left to the general reader."""
+    import struct
+    import wave
+
+    from speechsplit_b200.make_spect_f0 import read_wav, read_wav_pcm16
+    rng = np.random.default_rng(11)
+    v = rng.integers(-32768, 32768, 777).astype("<i2")
+    fmt = struct.pack("<HHIIHH", 1, 1, 16000, 32000, 2, 16)
+    plain = tmp_path / "plain.wav"
+    with wave.open(str(plain), "wb") as w:
+        w.setnchannels(1), w.setsampwidth(2), w.setframerate(16000)
+        w.writeframes(v.tobytes())
+    x, fs = read_wav_pcm16(str(plain))
+    assert fs == 16000 and x.dtype == np.int16 and np.array_equal(x, v) and not x.flags.writeable
+    # LIST chunk of odd size in front (pad byte), a trailing chunk behind the data
+    p = tmp_path / "chunks.wav"
+    p.write_bytes(_riff([(b"LIST", b"INFOabc"), (b"fmt ", fmt), (b"fact", b"\1\0\0\0"), (b"data", v.tobytes()), (b"cue ", b"xy")]))
+    x, fs = read_wav_pcm16(str(p))
+    assert fs == 16000 and np.array_equal(x, v)
+    with wave.open(str(p), "rb") as w:
+        assert np.array_equal(np.frombuffer(w.readframes(w.getnframes()), "<i2"), x)
+    # extensible format with the PCM sub-format GUID
+    ext = struct.pack("<HHIIHHHHIH", 0xFFFE, 1, 16000, 32000, 2, 16, 22, 16, 4, 1) + bytes.fromhex("000000001000800000aa00389b71")
+    assert len(ext) == 40
+    p = tmp_path / "ext.wav"
+    p.write_bytes(_riff([(b"fmt ", ext), (b"data", v.tobytes())]))
+    x, fs = read_wav_pcm16(str(p))
+    assert fs == 16000 and np.array_equal(x, v)
+    # truncated file: the data chunk claims 1554 bytes, 1001 are there -> 500 whole samples
+    raw = _riff([(b"fmt ", fmt), (b"data", v.tobytes())])
+    p = tmp_path / "trunc.wav"
+    p.write_bytes(raw[:len(raw) - 553])
+    x, _ = read_wav_pcm16(str(p))
+    assert np.array_equal(x, v[:500])
+    # an empty data chunk is an empty utterance, not an error here (ssfe_extract refuses it with its own message)
+    p = tmp_path / "empty.wav"
+    p.write_bytes(_riff([(b"fmt ", fmt), (b"data", b"")]))
+    x, _ = read_wav_pcm16(str(p))
+    assert x.shape == (0,)
+    # not for the fast path: stereo, 8-bit, float, data before fmt, not RIFF at all, a short file
+    for name, chunks in [("st", [(b"fmt ", struct.pack("<HHIIHH", 1, 2, 16000, 64000, 4, 16)), (b"data", v.tobytes()[:776 * 2])]),
+                         ("u8", [(b"fmt ", struct.pack("<HHIIHH", 1, 1, 16000, 16000, 1, 8)), (b"data", b"\x80" * 10)]),
+                         ("f32", [(b"fmt ", struct.pack("<HHIIHH", 3, 1, 16000, 64000, 4, 32)), (b"data", b"\0" * 16)]),
+                         ("nofmt", [(b"data", v.tobytes())])]:
+        q = tmp_path / (name + ".wav")
+        q.write_bytes(_riff(chunks))
+        assert read_wav_pcm16(str(q)) is None
+    (tmp_path / "junk.wav").write_bytes(b"OggS" + b"\0" * 64)
+    (tmp_path / "tiny.wav").write_bytes(b"RIFF")
+    assert read_wav_pcm16(str(tmp_path / "junk.wav")) is None and read_wav_pcm16(str(tmp_path / "tiny.wav")) is None
+    # ... and read_wav hands those to the general reader: stereo is refused there, 8-bit comes back as float64
+    with pytest.raises(ValueError):
+        read_wav(str(tmp_path / "st.wav"))
+    x, _ = read_wav(str(tmp_path / "u8.wav"))
+    assert x.dtype == np.float64 and np.array_equal(x, np.zeros(10))
+
+
+def test_save_npy_is_np_save_byte_for_byte(tmp_path):
+    """make_spect_f0.py:71-74 writes with np.save(..., allow_pickle=False); save_npy must leave the same bytes (NPY v1.0
+    header included) for the shapes the script writes, for views, empty arrays and paths with or without '.npy'."""
+    from speechsplit_b200.make_spect_f0 import save_npy
+    rng = np.random.default_rng(5)
+    big = rng.random((300, 80)).astype(np.float32)
+    cases = [big[:188], big[17:18], big[:0], big[:, 3].copy(), big[:, 3], big[::2], rng.random(188).astype(np.float32),
+             np.arange(7, dtype=np.int64), rng.random((4, 3, 2))]
+    for i, a in enumerate(cases * 2):                      # twice: the second round takes the cached headers
+        ref = tmp_path / ("ref%d.npy" % i)
+        np.save(ref, a, allow_pickle=False)
+        got = tmp_path / ("got%d" % i)
+        save_npy(str(got) + (".npy" if i & 1 else ""), a)
+        assert (tmp_path / ("got%d.npy" % i)).read_bytes() == ref.read_bytes(), i
+        assert np.array_equal(np.load(tmp_path / ("got%d.npy" % i), allow_pickle=False), a)
+    with pytest.raises(ValueError):
+        save_npy(str(tmp_path / "o"), np.array([{}], dtype=object))
+
+
+def test_script_form_io_threads_give_the_same_trees(tmp_path, monkeypatch):
+    """The inline file handling (default) and the opt-in thread pool write identical trees."""
+    import pickle
+    import wave
+
+    from speechsplit_b200 import make_spect_f0 as script
+    root = tmp_path / "wavs"
+    rng = np.random.default_rng(2)
+    for spk in ("p226", "p231", "p240"):
+        (root / spk).mkdir(parents=True)
+        for k in range(7):
+            with wave.open(str(root / spk / ("%s_%03d.wav" % (spk, k + 1))), "wb") as w:
+                w.setnchannels(1), w.setsampwidth(2), w.setframerate(16000)
+                w.writeframes(rng.integers(-3000, 3000, int(rng.integers(2000, 9000))).astype("<i2").tobytes())
+    with open(tmp_path / "spk2gen.pkl", "wb") as f:
+        pickle.dump({"p226": "M", "p231": "F", "p240": "F"}, f)
+    trees = []
+    for threads in (1, 4):
+        fake = _RecordingFrontEnd()
+        out = tmp_path / ("t%d" % threads)
+        st = {}
+        script.make_spect_f0(str(root), str(out / "spmel"), str(out / "raptf0"), str(tmp_path / "spk2gen.pkl"),
+                             verbose=False, io_threads=threads, frontend=fake, stats=st)
+        assert st["files"] == 21 and st["calls"] == 1 and len(fake.calls) == 1
+        trees.append({os.path.relpath(os.path.join(d, f), out): open(os.path.join(d, f), "rb").read()
+                      for d, _, fs in os.walk(out) for f in fs})
+    assert len(trees[0]) == 42 and trees[0] == trees[1]
