@@ -2,13 +2,15 @@
 
     python -m speechsplit_b200.make_spect_f0 [--root assets/wavs] [--out assets/spmel]
                                              [--out-f0 assets/raptf0] [--spk2gen assets/spk2gen.pkl]
+                                             [--device N] [--io-threads N]
 
 Same inputs and outputs as the reference (make_spect_f0.py:19-25,71-74): ``<root>/<spk>/*.wav``
 at 16 kHz mono, a pickled dict speaker -> 'M' / 'F', speaker directories named ``p<int>``;
 writes ``<out>/<spk>/<utt>.npy`` (T, 80) float32 and ``<out-f0>/<spk>/<utt>.npy`` (T,) float32
 with ``np.save(..., allow_pickle=False)``.  The per-utterance loop body (:50-67) runs as one
-``ssfe_extract`` call per group of speakers; file I/O stays on the host (stdlib ``wave``; the
-reference's ``soundfile`` is used when importable).
+``ssfe_extract`` call per group of speakers; file I/O stays on the host (mono 16-bit PCM through
+``read_wav_pcm16``, anything else through the reference's ``soundfile`` when importable, else stdlib
+``wave`` / scipy; NPY v1.0 through ``save_npy``).
 """
 import argparse
 import io
@@ -242,8 +244,10 @@ def main():
     ap.add_argument("--out-f0", default="assets/raptf0")
     ap.add_argument("--spk2gen", default="assets/spk2gen.pkl")
     ap.add_argument("--device", type=int, default=None)
+    ap.add_argument("--io-threads", type=int, default=1,
+                    help="> 1: WAV reads and NPY writes through a thread pool (worth it on slow file systems only)")
     a = ap.parse_args()
-    make_spect_f0(a.root, a.out, a.out_f0, a.spk2gen, a.device)
+    make_spect_f0(a.root, a.out, a.out_f0, a.spk2gen, a.device, io_threads=a.io_threads)
 
 
 if __name__ == "__main__":
