@@ -96,3 +96,37 @@ def test_gpu_quantiser_equals_oracle_on_arbitrary_input(vals, dtype):
     enc, idx = utils.quantize_f0_numpy(x)
     renc, ridx = rp.quantize_f0_numpy(x)
     assert np.array_equal(idx, ridx) and np.array_equal(enc, renc)
+
+
+_chunk_st = st.tuples(st.sampled_from([b"LIST", b"fact", b"cue ", b"bext", b"JUNK", b"id3 "]), st.binary(min_size=0, max_size=37))
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(_chunk_st, max_size=3), st.lists(_chunk_st, max_size=2), st.lists(_chunk_st, max_size=2),
+       st.binary(min_size=0, max_size=401), st.sampled_from([8000, 16000, 22050, 48000]))
+def test_read_wav_pcm16_agrees_with_the_stdlib_reader(before, between, after, payload, fs):
+    """Arbitrary RIFF layouts around a mono 16-bit PCM payload (extra chunks of odd and even size before the format
+    chunk, between it and the data, and behind it; odd payload sizes): read_wav_pcm16 returns what ``wave`` returns."""
+    import io
+    import os
+    import struct
+    import tempfile
+    import wave
+
+    from speechsplit_b200.make_spect_f0 import read_wav_pcm16
+    fmt = struct.pack("<HHIIHH", 1, 1, fs, 2 * fs, 2, 16)
+    chunks = list(before) + [(b"fmt ", fmt)] + list(between) + [(b"data", payload)] + list(after)
+    body = b"WAVE" + b"".join(c + len(d).to_bytes(4, "little") + d + (b"\0" if len(d) & 1 else b"") for c, d in chunks)
+    blob = b"RIFF" + len(body).to_bytes(4, "little") + body
+    with wave.open(io.BytesIO(blob), "rb") as w:
+        ref = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+        ref_fs = w.getframerate()
+    fd, path = tempfile.mkstemp(suffix=".wav")
+    try:
+        with os.fdopen(fd, "wb") as fh:
+            fh.write(blob)
+        got = read_wav_pcm16(path)
+    finally:
+        os.unlink(path)
+    assert got is not None and got[1] == ref_fs == fs
+    assert got[0].dtype == np.int16 and np.array_equal(got[0], ref)
